@@ -1,0 +1,671 @@
+// libb200dock: handle, workspace, weight upload and the per-step orchestration behind the C ABI
+// declared in include/b200dock.h.  Everything is launched on the caller's stream with fixed-size
+// grids that read their extents from device memory, so one evaluation needs no host round trip.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "graph.cuh"
+#include "embed.cuh"
+#include "conv.cuh"
+#include "conv_tc.cuh"
+#include "heads.cuh"
+#include "pose.cuh"
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t _e = (call);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                    \
+      return B200_ERR_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+namespace {
+
+struct Buf {
+  void* p = nullptr; size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ConvWs {                 // per edge family: lig, atom, al, la, tor, sc
+  int T = 0; int cap = 0; int z_max = 0;
+  Buf counts, seg, es, ed, eaux, emb, sh, H1, Zt, msg;
+};
+
+struct ConvW {                  // views into the device weight blob
+  const float *W1t, *b1, *W2p; LnParams ln;
+};
+
+}  // namespace
+
+struct B200Handle {
+  int device = 0;
+  std::string err;
+  B200Config cfg;
+  std::vector<std::vector<int32_t>> hold_i; std::vector<std::vector<float>> hold_f;
+  DevPlan dplans[B200_N_PLANS];
+  std::vector<void*> plan_allocs;
+  int* d_tor_cg_ijk = nullptr; float* d_tor_cg_val = nullptr;
+  float* d_blob = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
+  ConvW convw[26];
+  // workspace
+  ConvWs cw[6];
+  Buf pre[6], h_lig, h_atom, jmax_lig, jmax_atom, centre, cmsg, s_tr, s_rot, s_tor, s_sc, atom14, errflag;
+  Buf c_temb, c_trs, c_rotn, c_torn, c_scn, temb_steps;
+  // host-batch path
+  Buf pinned_in, dev_in, dev_noise, dev_lig_out, dev_a14_out, pinned_out;
+  int64_t launches = 0;
+  int64_t last_counts[5] = {0, 0, 0, 0, 0};
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tp_events;
+  std::vector<cudaEvent_t> event_pool; size_t event_used = 0;
+  B200Batch last_batch; bool have_last = false;
+  int n_sms = 148;
+  int debug_layers = 6;
+};
+
+namespace {
+
+int ensure(B200Handle* h, Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return B200_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return B200_OK;
+}
+#define ENS(buf, bytes) do { int _r = ensure(h, buf, (size_t)(bytes)); if (_r) return _r; } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline int grid_for(long long n, int threads, int max_blocks) {
+  long long g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+template <typename T>
+int upload(B200Handle* h, const T* src, size_t n, T** dst) {
+  CK(cudaMalloc((void**)dst, n * sizeof(T) + 16));
+  h->plan_allocs.push_back(*dst);
+  if (n) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return B200_OK;
+}
+
+int plan_of_layer(int l) { return l < 3 ? l : 3; }
+
+cudaEvent_t get_event(B200Handle* h) {
+  if (h->event_used == h->event_pool.size()) {
+    cudaEvent_t e; cudaEventCreate(&e); h->event_pool.push_back(e);
+  }
+  return h->event_pool[h->event_used++];
+}
+
+int setup_workspace(B200Handle* h, const B200Batch& b) {
+  if (b.B <= 0 || b.N_l <= 0 || b.N_a <= 0 || b.N_r <= 0) FAIL(B200_ERR_INVALID, "empty batch");
+  if (b.max_lig_atoms > POSE_MAX_ATOMS) FAIL(B200_ERR_INVALID, "ligand larger than 256 heavy atoms is not supported");
+  auto r128 = [](long long x) { return (int)(((x + 127) / 128) * 128 + 128); };
+  long long caps[6];
+  caps[0] = 33LL * b.N_l + b.E_b;
+  caps[1] = std::min<long long>(64LL * b.N_a, b.atom_pairs);
+  caps[2] = caps[3] = b.cross_pairs;
+  caps[4] = 32LL * b.n_tor;
+  caps[5] = 32LL * b.n_sc;
+  int Ts[6] = {b.N_l, b.N_a, b.N_l, b.N_a, b.n_tor, b.n_sc};
+  int zmax[6] = {624, 624, 624, 624, 144, 144};
+  for (int c = 0; c < 6; ++c) {
+    ConvWs& w = h->cw[c];
+    w.T = Ts[c]; w.cap = r128(caps[c]); w.z_max = zmax[c];
+    ENS(w.counts, (size_t)(w.T + 1) * 4); ENS(w.seg, (size_t)(w.T + 2) * 4);
+    ENS(w.es, (size_t)w.cap * 4); ENS(w.ed, (size_t)w.cap * 4);
+    if (c == 0) ENS(w.eaux, (size_t)w.cap * 4);
+    ENS(w.emb, (size_t)w.cap * NSC * 4); ENS(w.sh, (size_t)w.cap * 9 * 4);
+    ENS(w.H1, (size_t)w.cap * KP * 4); ENS(w.Zt, (size_t)w.cap * w.z_max * 4); ENS(w.msg, (size_t)w.cap * HS * 4);
+  }
+  for (int m = 0; m < 6; ++m) ENS(h->pre[m], (size_t)b.B * NSC * 4);
+  ENS(h->h_lig, (size_t)b.N_l * HS * 4); ENS(h->h_atom, (size_t)b.N_a * HS * 4);
+  ENS(h->jmax_lig, (size_t)b.N_l * 4); ENS(h->jmax_atom, (size_t)b.N_a * 4);
+  ENS(h->centre, (size_t)b.B * 3 * 4); ENS(h->cmsg, (size_t)b.N_l * 12 * 4);
+  ENS(h->s_tr, (size_t)b.B * 3 * 4); ENS(h->s_rot, (size_t)b.B * 3 * 4);
+  ENS(h->s_tor, (size_t)(b.n_tor + 1) * 4); ENS(h->s_sc, (size_t)(b.n_sc + 1) * 4);
+  ENS(h->atom14, (size_t)b.N_r * 14 * 3 * 4);
+  ENS(h->errflag, 16);
+  ENS(h->c_temb, (size_t)b.B * SIG * 4); ENS(h->c_trs, (size_t)b.B * 4); ENS(h->c_rotn, (size_t)b.B * 4);
+  ENS(h->c_torn, (size_t)(b.n_tor + 1) * 4); ENS(h->c_scn, (size_t)(b.n_sc + 1) * 4);
+  return B200_OK;
+}
+
+EdgeMlp edge_mlp(const B200Handle* h, int section, int n_bond, int n_sigma) {
+  EdgeMlp m; m.w = h->d_blob + h->off[section]; m.n_bond = n_bond; m.n_sigma = n_sigma; return m;
+}
+
+template <int KIND>
+int build_graph(B200Handle* h, const GraphArgs& G, ConvWs& w, cudaStream_t st) {
+  if (w.T == 0) return B200_OK;
+  k_graph_count<KIND><<<grid_for(w.T, 128, 148 * 8), 128, 0, st>>>(G, w.T, w.counts.as<int>());
+  k_scan<<<1, 1024, 0, st>>>(w.counts.as<int>(), w.T, w.seg.as<int>());
+  k_graph_fill<KIND><<<grid_for(w.T, 128, 148 * 8), 128, 0, st>>>(G, w.T, w.seg.as<int>(), w.cap - 128, w.es.as<int>(),
+                                                               w.ed.as<int>(), KIND == G_LIG ? w.eaux.as<int>() : nullptr,
+                                                               h->errflag.as<int>());
+  h->launches += 3;
+  return B200_OK;
+}
+
+template <int KIND>
+void edge_feat(B200Handle* h, const B200Batch& b, ConvWs& w, EdgeMlp mlp, const float* pre, float stop, cudaStream_t st) {
+  if (w.T == 0) return;
+  EdgeFeatArgs A{};
+  A.n_edges = w.seg.as<int>() + w.T; A.es = w.es.as<int>(); A.ed = w.ed.as<int>(); A.eaux = w.eaux.as<int>();
+  if (KIND == G_LIG) { A.pos_s = b.lig_pos; A.pos_d = b.lig_pos; A.batch_for_pre = b.lig_batch; }
+  if (KIND == G_ATOM) { A.pos_s = b.rec_atm_pos; A.pos_d = b.rec_atm_pos; A.batch_for_pre = b.atom_batch; }
+  if (KIND == G_AL) { A.pos_s = b.lig_pos; A.pos_d = b.rec_atm_pos; A.batch_for_pre = b.lig_batch; }
+  if (KIND == G_LA) { A.pos_s = b.rec_atm_pos; A.pos_d = b.lig_pos; A.batch_for_pre = b.lig_batch; }
+  if (KIND == G_TOR) { A.pos_s = b.lig_pos; A.pos_d = b.lig_pos; A.bonds = b.tor_bonds; }
+  if (KIND == G_SC) { A.pos_s = b.rec_atm_pos; A.pos_d = b.rec_atm_pos; A.bonds = b.sc_bonds; }
+  A.pre = pre; A.lig_edge_feat = b.lig_edge_feat; A.mlp = mlp; A.stop = stop;
+  A.emb = w.emb.as<float>(); A.sh = w.sh.as<float>();
+  A.cg_ijk = h->d_tor_cg_ijk; A.cg_val = h->d_tor_cg_val;
+  for (int i = 0; i < 4; ++i) A.cg_off[i] = h->cfg.tor_cg_off[i];
+  size_t smem = (size_t)((mlp.n_bond + SIG) * NSC + NSC * NSC + 2 * NSC + SIG) * 4;
+  k_edge_feat<KIND><<<148 * 4, 128, smem, st>>>(A);
+  h->launches += 1;
+}
+
+int launch_tp(B200Handle* h, const ConvLaunch& L, cudaStream_t st) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
+  int rc = B200_OK;
+  if (h->cfg.conv_kernel == 0) {
+    k_conv_tp_simt<<<h->n_sms, TP_THREADS, TP_SMEM, st>>>(L);
+  } else {
+    rc = launch_conv_tc(L, h->cfg.conv_kernel, h->n_sms, st);
+  }
+  if (h->profiling) { cudaEventRecord(e1, st); h->tp_events.push_back({e0, e1}); }
+  h->launches += 1;
+  if (rc) FAIL(B200_ERR_CUDA, "tcgen05 conv launch failed");
+  return B200_OK;
+}
+
+ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* tabA, const float* tabB, int mode,
+                   const int* bonds, int sh_stride) {
+  ConvArgs C{};
+  C.n_edges = w.seg.as<int>() + w.T; C.es = w.es.as<int>(); C.ed = w.ed.as<int>();
+  C.emb = w.emb.as<float>(); C.sh = w.sh.as<float>(); C.sh_stride = sh_stride;
+  C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode; C.plan = plan;
+  C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1; C.W2p = h->convw[widx].W2p;
+  C.H1 = w.H1.as<float>(); C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
+  return C;
+}
+
+// One evaluation of the score network on device-resident batch + conditioning.
+int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr, float* rot, float* tor, float* sc,
+                 cudaStream_t st) {
+  if (!h->weights) FAIL(B200_ERR_STATE, "weights not loaded");
+  const float* W = h->d_blob;
+  const std::vector<int64_t>& off = h->off;
+  // ---- sigma pre-activations
+  {
+    PreArgs P{};
+    int secs[6] = {B200_W_LIG_NODE, B200_W_LIG_EDGE, B200_W_ATOM_EMB, B200_W_ATOM_EDGE, B200_W_LA_EDGE, B200_W_CENTER_EDGE};
+    int ins[6] = {59, 74, 0, 64, 64, 64};
+    int sig_off[6] = {27, 10, 48, 0, 0, 0};
+    for (int m = 0; m < 6; ++m) {
+      const float* rec = W + off[secs[m]];
+      if (m == 2) { P.w0t[m] = rec + 86 * NSC; P.b0[m] = nullptr; }           // scalar_lin, no bias
+      else { P.w0t[m] = rec; P.b0[m] = rec + (size_t)ins[m] * NSC; }
+      P.sig_off[m] = sig_off[m]; P.out[m] = h->pre[m].as<float>();
+    }
+    P.n = 6;
+    k_graph_pre<<<dim3(b.B, 6), 64, 0, st>>>(P, c.time_emb, b.B);
+    h->launches += 1;
+  }
+  k_lig_node_embed<<<grid_for(b.N_l, 128, 148 * 4), 128, 0, st>>>(b.lig_node, b.lig_batch, b.N_l, W + off[B200_W_LIG_NODE],
+                                                                   h->pre[0].as<float>(), h->h_lig.as<float>());
+  k_atom_node_embed<<<grid_for(b.N_a, 128, 148 * 4), 128, 0, st>>>(b.pocket_feat, b.atom_batch, b.N_a, W + off[B200_W_ATOM_EMB],
+                                                                    h->pre[2].as<float>(), h->h_atom.as<float>());
+  h->launches += 2;
+  // ---- graphs
+  GraphArgs G{};
+  G.lig_pos = b.lig_pos; G.lig_batch = b.lig_batch; G.lig_ptr = b.lig_ptr; G.N_l = b.N_l;
+  G.atom_pos = b.rec_atm_pos; G.atom_batch = b.atom_batch; G.atom_ptr = b.atom_ptr; G.N_a = b.N_a;
+  G.pocket_feat = b.pocket_feat; G.tr_sigma = c.tr_sigma;
+  G.bond_ptr = b.bond_ptr; G.bond_dst = b.bond_dst; G.bond_eid = b.bond_eid;
+  G.tor_bonds = b.tor_bonds; G.n_tor = b.n_tor; G.sc_bonds = b.sc_bonds; G.n_sc = b.n_sc;
+  G.lig_jmax = h->jmax_lig.as<int>(); G.atom_jmax = h->jmax_atom.as<int>();
+  k_radius_cap<<<grid_for(b.N_l, 128, 148 * 8), 128, 0, st>>>(b.lig_pos, b.lig_batch, b.lig_ptr, b.N_l, 25.0f, 33, h->jmax_lig.as<int>());
+  k_radius_cap<<<grid_for(b.N_a, 128, 148 * 8), 128, 0, st>>>(b.rec_atm_pos, b.atom_batch, b.atom_ptr, b.N_a, 16.0f, 1001, h->jmax_atom.as<int>());
+  h->launches += 2;
+  int rc;
+  if ((rc = build_graph<G_LIG>(h, G, h->cw[0], st))) return rc;
+  if ((rc = build_graph<G_ATOM>(h, G, h->cw[1], st))) return rc;
+  if ((rc = build_graph<G_AL>(h, G, h->cw[2], st))) return rc;
+  if ((rc = build_graph<G_LA>(h, G, h->cw[3], st))) return rc;
+  edge_feat<G_LIG>(h, b, h->cw[0], edge_mlp(h, B200_W_LIG_EDGE, 10, 32), h->pre[1].as<float>(), 5.0f, st);
+  edge_feat<G_ATOM>(h, b, h->cw[1], edge_mlp(h, B200_W_ATOM_EDGE, 0, 32), h->pre[3].as<float>(), 4.0f, st);
+  edge_feat<G_AL>(h, b, h->cw[2], edge_mlp(h, B200_W_LA_EDGE, 0, 32), h->pre[4].as<float>(), 32.0f, st);
+  edge_feat<G_LA>(h, b, h->cw[3], edge_mlp(h, B200_W_LA_EDGE, 0, 32), h->pre[4].as<float>(), 32.0f, st);
+  // ---- six interaction layers
+  float* hl = h->h_lig.as<float>(); float* ha = h->h_atom.as<float>();
+  for (int l = 0; l < h->debug_layers; ++l) {
+    const int plan = plan_of_layer(l);
+    ConvLaunch L{};
+    L.n = 4;
+    L.c[0] = conv_args(h, h->cw[0], 0 * 6 + l, plan, hl, hl, 0, nullptr, 9);     // lig
+    L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9);     // atom
+    L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9);     // al: target lig, gather atom
+    L.c[3] = conv_args(h, h->cw[3], 3 * 6 + l, plan, ha, hl, 0, nullptr, 9);     // la: target atom, gather lig
+    k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
+    h->launches += 1;
+    if ((rc = launch_tp(h, L, st))) return rc;
+    NodeUpdateArgs U{};
+    U.plan = plan;
+    U.N = b.N_l; U.h = hl;
+    U.seg[0] = h->cw[0].seg.as<int>(); U.msg[0] = h->cw[0].msg.as<float>(); U.ln[0] = h->convw[0 * 6 + l].ln;
+    U.seg[1] = h->cw[2].seg.as<int>(); U.msg[1] = h->cw[2].msg.as<float>(); U.ln[1] = h->convw[2 * 6 + l].ln;
+    k_node_update<<<grid_for(b.N_l, 8, 148 * 8), 256, 0, st>>>(U);
+    U.N = b.N_a; U.h = ha;
+    U.seg[0] = h->cw[1].seg.as<int>(); U.msg[0] = h->cw[1].msg.as<float>(); U.ln[0] = h->convw[1 * 6 + l].ln;
+    U.seg[1] = h->cw[3].seg.as<int>(); U.msg[1] = h->cw[3].msg.as<float>(); U.ln[1] = h->convw[3 * 6 + l].ln;
+    k_node_update<<<grid_for(b.N_a, 8, 148 * 8), 256, 0, st>>>(U);
+    h->launches += 2;
+  }
+  // ---- translation / rotation heads
+  {
+    k_centroid<<<cdiv(b.B, 64), 64, 0, st>>>(b.lig_pos, b.lig_ptr, b.B, h->centre.as<float>());
+    CenterArgs A{};
+    A.lig_pos = b.lig_pos; A.lig_batch = b.lig_batch; A.N_l = b.N_l; A.centre = h->centre.as<float>();
+    A.pre = h->pre[5].as<float>(); A.mlp = edge_mlp(h, B200_W_CENTER_EDGE, 0, 32); A.fc = W + off[B200_W_FINAL_FC];
+    A.h_lig = hl; A.cmsg = h->cmsg.as<float>();
+    k_center_edge<<<b.N_l, 128, 0, st>>>(A);
+    CenterHeadArgs H{};
+    H.cmsg = h->cmsg.as<float>(); H.lig_ptr = b.lig_ptr; H.B = b.B; H.ln = W + off[B200_W_FINAL_LN];
+    H.tr_mlp = W + off[B200_W_TR_FINAL]; H.rot_mlp = W + off[B200_W_ROT_FINAL];
+    H.time_emb = c.time_emb; H.tr_sigma = c.tr_sigma; H.rot_score_norm = c.rot_score_norm; H.tr = tr; H.rot = rot;
+    k_center_head<<<cdiv(b.B, 64), 64, 0, st>>>(H);
+    h->launches += 3;
+  }
+  // ---- pseudo-torque heads (ligand torsions, side-chain chi)
+  for (int which = 0; which < 2; ++which) {
+    ConvWs& w = h->cw[4 + which];
+    if (w.T == 0) continue;
+    if (which == 0) { if ((rc = build_graph<G_TOR>(h, G, w, st))) return rc; }
+    else { if ((rc = build_graph<G_SC>(h, G, w, st))) return rc; }
+    if (which == 0) edge_feat<G_TOR>(h, b, w, edge_mlp(h, B200_W_TOR_EDGE, 0, 0), nullptr, 5.0f, st);
+    else edge_feat<G_SC>(h, b, w, edge_mlp(h, B200_W_SC_EDGE, 0, 0), nullptr, 4.0f, st);
+    const float* tab = which == 0 ? hl : ha;
+    ConvLaunch L{};
+    L.n = 1;
+    L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8);
+    k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
+    h->launches += 1;
+    if ((rc = launch_tp(h, L, st))) return rc;
+    TorHeadArgs T{};
+    T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
+    T.mlp = W + off[which == 0 ? B200_W_TOR_FINAL : B200_W_SC_FINAL];
+    T.norm2 = which == 0 ? c.tor_score_norm2 : c.sc_tor_score_norm2; T.out = which == 0 ? tor : sc;
+    k_tor_head<<<grid_for(w.T, 8, 148 * 8), 256, 0, st>>>(T);
+    h->launches += 1;
+  }
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+__global__ void k_fill_cond(int B, int n_tor, int n_sc, const float* __restrict__ temb, B200Step s, float* c_temb,
+                            float* c_trs, float* c_rotn, float* c_torn, float* c_scn) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * SIG) c_temb[i] = temb[i % SIG];
+  if (i < B) { c_trs[i] = s.tr_sigma; c_rotn[i] = s.rot_score_norm; }
+  if (i < n_tor) c_torn[i] = s.tor_score_norm2;
+  if (i < n_sc) c_scn[i] = s.sc_tor_score_norm2;
+}
+
+int check_errflag(B200Handle* h, cudaStream_t st) {
+  int flag = 0;
+  CK(cudaMemcpyAsync(&flag, h->errflag.p, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (flag) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "edge list of graph kind %d overflowed its workspace capacity", flag - 1);
+    FAIL(B200_ERR_CAPACITY, msg);
+  }
+  int64_t* lc = h->last_counts;
+  int idx[5] = {0, 1, 2, 4, 5};
+  for (int i = 0; i < 5; ++i) {
+    ConvWs& w = h->cw[idx[i]];
+    int v = 0;
+    if (w.T > 0) CK(cudaMemcpy(&v, w.seg.as<int>() + w.T, 4, cudaMemcpyDeviceToHost));
+    lc[i] = v;
+  }
+  return B200_OK;
+}
+
+int sample_device(B200Handle* h, B200Batch& b, const B200Step* steps, int n_steps, const float* time_emb_host,
+                  const float* noise, float* lig_traj, float* atom14_out, float* atom14_traj, cudaStream_t st) {
+  int rc = setup_workspace(h, b);
+  if (rc) return rc;
+  ENS(h->temb_steps, (size_t)n_steps * SIG * 4);
+  CK(cudaMemcpyAsync(h->temb_steps.p, time_emb_host, (size_t)n_steps * SIG * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->errflag.p, 0, 16, st));
+  const size_t nstride = (size_t)6 * b.B + b.n_tor + b.n_sc;
+  const int maxn = std::max(std::max(b.B * SIG, b.n_tor), b.n_sc);
+  for (int s = 0; s < n_steps; ++s) {
+    k_fill_cond<<<cdiv(maxn, 256), 256, 0, st>>>(b.B, b.n_tor, b.n_sc, h->temb_steps.as<float>() + (size_t)s * SIG, steps[s],
+                                                 h->c_temb.as<float>(), h->c_trs.as<float>(), h->c_rotn.as<float>(),
+                                                 h->c_torn.as<float>(), h->c_scn.as<float>());
+    h->launches += 1;
+    B200Cond c{h->c_temb.as<float>(), h->c_trs.as<float>(), h->c_rotn.as<float>(), h->c_torn.as<float>(), h->c_scn.as<float>()};
+    rc = score_device(h, b, c, h->s_tr.as<float>(), h->s_rot.as<float>(), h->s_tor.as<float>(), h->s_sc.as<float>(), st);
+    if (rc) return rc;
+    const float* z = noise + (size_t)s * nstride;
+    PoseArgs P{};
+    P.B = b.B; P.lig_pos = b.lig_pos; P.lig_ptr = b.lig_ptr; P.tor_bonds = b.tor_bonds; P.tor_ptr = b.tor_ptr;
+    P.rot_mask = b.rot_mask; P.rot_mask_off = b.rot_mask_off;
+    P.tr_score = h->s_tr.as<float>(); P.rot_score = h->s_rot.as<float>(); P.tor_score = h->s_tor.as<float>();
+    P.z_tr = z; P.z_rot = z + 3 * b.B; P.z_tor = z + 6 * b.B; P.st = steps[s];
+    P.lig_traj_out = lig_traj ? lig_traj + (size_t)s * b.N_l * 3 : nullptr;
+    k_lig_pose_update<<<b.B, 32, 0, st>>>(P);
+    SideChainArgs S{};
+    S.N_r = b.N_r; S.N_a = b.N_a; S.sequence = b.sequence; S.bb_t = b.backbone_transl; S.bb_R = b.backbone_rots;
+    S.default_frame = b.default_frame; S.rigid_pos = b.rigid_group_pos; S.torsion_angle = b.torsion_angle;
+    S.sc_index = b.sc_index; S.atom14_mask = b.atom14_mask; S.atom_slot = b.atom_slot;
+    S.sc_score = h->s_sc.as<float>(); S.z_sc = z + 6 * b.B + b.n_tor; S.st = steps[s]; S.apply_update = 1;
+    S.atom14 = (s == n_steps - 1 && atom14_out) ? atom14_out : h->atom14.as<float>();
+    S.atom14_traj = atom14_traj ? atom14_traj + (size_t)s * b.N_r * 42 : nullptr;
+    k_sidechain_update<<<cdiv(b.N_r, 64), 64, 0, st>>>(S);
+    k_gather_atoms<<<grid_for(b.N_a, 256, 148 * 4), 256, 0, st>>>(S.atom14, b.atom_slot, b.N_a, b.rec_atm_pos);
+    h->launches += 3;
+  }
+  CK(cudaGetLastError());
+  h->last_batch = b; h->have_last = true;
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200dock_version(void) { return "b200dock 0.1 (sm_100a)"; }
+
+const char* b200dock_last_error(const B200Handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
+  if (!cfg || !out) return B200_ERR_INVALID;
+  B200Handle* h = new B200Handle();
+  *out = h;
+  h->device = device;
+  h->cfg = *cfg;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->n_sms = prop.multiProcessorCount;
+  for (int p = 0; p < B200_N_PLANS; ++p) {
+    const B200ConvPlan& s = cfg->plans[p];
+    DevPlan& d = h->dplans[p];
+    memset(&d, 0, sizeof d);
+    d.n_paths = s.n_paths;
+    for (int i = 0; i < B200_MAX_PATHS; ++i) d.paths[i] = s.paths[i];
+    d.in_dim = s.in_dim; d.sh_dim = s.sh_dim; d.out_dim = s.out_dim; d.z_numel = s.z_numel; d.n_cols = s.n_cols;
+    d.n_blocks = s.n_blocks;
+    for (int i = 0; i < B200_MAX_BLOCKS; ++i) d.blocks[i] = s.blocks[i];
+    d.n_cg = s.n_cg; d.n_chunks = s.n_chunks;
+    int rc;
+    int *ijk, *cc, *cn, *cp; float* val;
+    if ((rc = upload(h, s.cg_ijk, (size_t)s.n_cg, &ijk))) return rc;
+    if ((rc = upload(h, s.cg_val, (size_t)s.n_cg, &val))) return rc;
+    if ((rc = upload(h, s.chunk_col, (size_t)s.n_chunks, &cc))) return rc;
+    if ((rc = upload(h, s.chunk_n, (size_t)s.n_chunks, &cn))) return rc;
+    if ((rc = upload(h, s.chunk_path, (size_t)s.n_chunks, &cp))) return rc;
+    d.cg_ijk = ijk; d.cg_val = val; d.chunk_col = cc; d.chunk_n = cn; d.chunk_path = cp;
+    // keep host copies for the tensor-core path (chunk tables are read on the host too)
+    h->hold_i.emplace_back(s.chunk_col, s.chunk_col + s.n_chunks);
+    h->hold_i.emplace_back(s.chunk_n, s.chunk_n + s.n_chunks);
+    h->hold_i.emplace_back(s.chunk_path, s.chunk_path + s.n_chunks);
+  }
+  CK(cudaMemcpyToSymbol(c_plans, h->dplans, sizeof(DevPlan) * B200_N_PLANS));
+  CK(cudaMemcpyToSymbol(c_atom14_group, cfg->atom14_group, sizeof(int) * 21 * 14));
+  int rc;
+  if ((rc = upload(h, cfg->tor_cg_ijk, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_ijk))) return rc;
+  if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
+  CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
+  CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+  if (conv_tc_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
+  return B200_OK;
+}
+
+void b200dock_destroy(B200Handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  auto fr = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
+  for (auto& w : h->cw) { fr(w.counts); fr(w.seg); fr(w.es); fr(w.ed); fr(w.eaux); fr(w.emb); fr(w.sh); fr(w.H1); fr(w.Zt); fr(w.msg); }
+  for (auto& b : h->pre) fr(b);
+  Buf* all[] = {&h->h_lig, &h->h_atom, &h->jmax_lig, &h->jmax_atom, &h->centre, &h->cmsg, &h->s_tr, &h->s_rot, &h->s_tor,
+                &h->s_sc, &h->atom14, &h->errflag, &h->c_temb, &h->c_trs, &h->c_rotn, &h->c_torn, &h->c_scn,
+                &h->temb_steps, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
+  for (Buf* b : all) fr(*b);
+  if (h->pinned_in.p) cudaFreeHost(h->pinned_in.p);
+  if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
+  for (void* p : h->plan_allocs) cudaFree(p);
+  if (h->d_blob) cudaFree(h->d_blob);
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  delete h;
+}
+
+int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int64_t* offsets, int n_sections) {
+  if (!h || !blob || !offsets) return B200_ERR_INVALID;
+  if (n_sections != B200_W_N_SECTIONS) FAIL(B200_ERR_INVALID, "unexpected number of weight sections");
+  CK(cudaSetDevice(h->device));
+  if (h->d_blob) CK(cudaFree(h->d_blob));
+  CK(cudaMalloc((void**)&h->d_blob, n * sizeof(float) + 1024));
+  CK(cudaMemcpy(h->d_blob, blob, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->blob_n = n;
+  h->off.assign(offsets, offsets + n_sections);
+  for (int i = 0; i < 26; ++i) {
+    int plan = i < 24 ? plan_of_layer(i % 6) : B200_PLAN_TOR;
+    const B200ConvPlan& P = h->cfg.plans[plan];
+    int nirr = 0, nsc = 0;
+    for (int b = 0; b < P.n_blocks; ++b) { nirr += P.blocks[b].mul; if (P.blocks[b].bias_off >= 0) nsc += P.blocks[b].mul; }
+    const float* r = h->d_blob + h->off[B200_W_CONV0 + i];
+    ConvW& w = h->convw[i];
+    w.W1t = r; r += 144 * 144;
+    w.b1 = r; r += 144;
+    w.W2p = r; r += (size_t)P.n_cols * KP;
+    w.ln.shift = r; r += nirr;
+    w.ln.weight = r; r += nirr;
+    w.ln.bias = r; r += nsc;
+    if ((size_t)(r - h->d_blob) > n) FAIL(B200_ERR_INVALID, "weight blob too small for its section table");
+    if (((uintptr_t)w.W2p & 15) != 0) FAIL(B200_ERR_INVALID, "conv record is not 16-byte aligned");
+  }
+  h->weights = true;
+  return B200_OK;
+}
+
+int b200dock_score(B200Handle* h, const B200Batch* batch, const B200Cond* cond, float* tr, float* rot, float* tor,
+                   float* sc, void* stream) {
+  if (!h || !batch || !cond) return B200_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  int rc = setup_workspace(h, *batch);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(h->errflag.p, 0, 16, st));
+  rc = score_device(h, *batch, *cond, tr, rot, tor ? tor : h->s_tor.as<float>(), sc ? sc : h->s_sc.as<float>(), st);
+  if (rc) return rc;
+  h->last_batch = *batch; h->have_last = true;
+  return check_errflag(h, st);
+}
+
+int b200dock_sample(B200Handle* h, B200Batch* batch, const B200Step* steps, int n_steps, const float* time_emb,
+                    const float* noise, float* lig_traj, float* atom14_out, float* atom14_traj, void* stream) {
+  if (!h || !batch || !steps || !time_emb || !noise || n_steps <= 0) return B200_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  int rc = sample_device(h, *batch, steps, n_steps, time_emb, noise, lig_traj, atom14_out, atom14_traj, st);
+  if (rc) return rc;
+  return check_errflag(h, st);
+}
+
+int b200dock_sample_host(B200Handle* h, const B200Batch* hb, const B200Step* steps, int n_steps, const float* time_emb,
+                         const float* noise, float* lig_out, float* atom14_out, uint64_t* h2d_bytes,
+                         uint64_t* d2h_bytes, void* stream) {
+  if (!h || !hb || !steps || !time_emb || !noise || !lig_out || !atom14_out || n_steps <= 0) return B200_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  h->launches = 0;
+  const B200Batch& b = *hb;
+  // ---- lay all inputs out in one pinned arena, one H2D copy
+  struct Item { const void* src; size_t bytes; size_t off; };
+  std::vector<Item> items;
+  size_t total = 0;
+  auto add = [&](const void* p, size_t bytes) { size_t o = total; items.push_back({p, bytes, o}); total += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t nstride = (size_t)6 * b.B + b.n_tor + b.n_sc;
+  size_t o_lig_node = add(b.lig_node, (size_t)b.N_l * 27 * 4), o_lig_pos = add(b.lig_pos, (size_t)b.N_l * 12),
+         o_lig_ptr = add(b.lig_ptr, (size_t)(b.B + 1) * 4), o_lig_batch = add(b.lig_batch, (size_t)b.N_l * 4),
+         o_bond_ptr = add(b.bond_ptr, (size_t)(b.N_l + 1) * 4), o_bond_dst = add(b.bond_dst, (size_t)b.E_b * 4),
+         o_bond_eid = add(b.bond_eid, (size_t)b.E_b * 4), o_ef = add(b.lig_edge_feat, (size_t)b.E_b * 40),
+         o_tb = add(b.tor_bonds, (size_t)b.n_tor * 8), o_tp = add(b.tor_ptr, (size_t)(b.B + 1) * 4),
+         o_rm = add(b.rot_mask, (size_t)b.rot_mask_bytes), o_rmo = add(b.rot_mask_off, (size_t)b.n_tor * 8),
+         o_pf = add(b.pocket_feat, (size_t)b.N_a * 20), o_rp = add(b.rec_atm_pos, (size_t)b.N_a * 12),
+         o_ap = add(b.atom_ptr, (size_t)(b.B + 1) * 4), o_ab = add(b.atom_batch, (size_t)b.N_a * 4),
+         o_as = add(b.atom_slot, (size_t)b.N_a * 4), o_rptr = add(b.res_ptr, (size_t)(b.B + 1) * 4),
+         o_m14 = add(b.atom14_mask, (size_t)b.N_r * 14), o_seq = add(b.sequence, (size_t)b.N_r * 4),
+         o_bt = add(b.backbone_transl, (size_t)b.N_r * 12), o_bR = add(b.backbone_rots, (size_t)b.N_r * 36),
+         o_df = add(b.default_frame, (size_t)b.N_r * 8 * 64), o_rg = add(b.rigid_group_pos, (size_t)b.N_r * 14 * 12),
+         o_ta = add(b.torsion_angle, (size_t)b.N_r * 20), o_scb = add(b.sc_bonds, (size_t)b.n_sc * 8),
+         o_sci = add(b.sc_index, (size_t)b.N_r * 16), o_noise = add(noise, nstride * n_steps * 4);
+  if (total > h->pinned_in.cap) {
+    if (h->pinned_in.p) CK(cudaFreeHost(h->pinned_in.p));
+    h->pinned_in.p = nullptr; h->pinned_in.cap = 0;
+    CK(cudaMallocHost(&h->pinned_in.p, total + total / 8));
+    h->pinned_in.cap = total + total / 8;
+  }
+  ENS(h->dev_in, total);
+  char* pin = (char*)h->pinned_in.p;
+  for (const Item& it : items) if (it.bytes) memcpy(pin + it.off, it.src, it.bytes);
+  CK(cudaMemcpyAsync(h->dev_in.p, pin, total, cudaMemcpyHostToDevice, st));
+  char* d = (char*)h->dev_in.p;
+  B200Batch db = b;
+  db.lig_node = (const float*)(d + o_lig_node); db.lig_pos = (float*)(d + o_lig_pos);
+  db.lig_ptr = (const int*)(d + o_lig_ptr); db.lig_batch = (const int*)(d + o_lig_batch);
+  db.bond_ptr = (const int*)(d + o_bond_ptr); db.bond_dst = (const int*)(d + o_bond_dst);
+  db.bond_eid = (const int*)(d + o_bond_eid); db.lig_edge_feat = (const float*)(d + o_ef);
+  db.tor_bonds = (const int*)(d + o_tb); db.tor_ptr = (const int*)(d + o_tp);
+  db.rot_mask = (const uint8_t*)(d + o_rm); db.rot_mask_off = (const int64_t*)(d + o_rmo);
+  db.pocket_feat = (const int*)(d + o_pf); db.rec_atm_pos = (float*)(d + o_rp);
+  db.atom_ptr = (const int*)(d + o_ap); db.atom_batch = (const int*)(d + o_ab); db.atom_slot = (const int*)(d + o_as);
+  db.res_ptr = (const int*)(d + o_rptr); db.atom14_mask = (const uint8_t*)(d + o_m14); db.sequence = (const int*)(d + o_seq);
+  db.backbone_transl = (const float*)(d + o_bt); db.backbone_rots = (const float*)(d + o_bR);
+  db.default_frame = (const float*)(d + o_df); db.rigid_group_pos = (const float*)(d + o_rg);
+  db.torsion_angle = (float*)(d + o_ta); db.sc_bonds = (const int*)(d + o_scb); db.sc_index = (const int*)(d + o_sci);
+  ENS(h->dev_a14_out, (size_t)b.N_r * 42 * 4);
+  int rc = sample_device(h, db, steps, n_steps, time_emb, (const float*)(d + o_noise), nullptr,
+                         h->dev_a14_out.as<float>(), nullptr, st);
+  if (rc) return rc;
+  const size_t out_bytes = (size_t)b.N_l * 12 + (size_t)b.N_r * 42 * 4;
+  if (out_bytes > h->pinned_out.cap) {
+    if (h->pinned_out.p) CK(cudaFreeHost(h->pinned_out.p));
+    h->pinned_out.p = nullptr; h->pinned_out.cap = 0;
+    CK(cudaMallocHost(&h->pinned_out.p, out_bytes + out_bytes / 8));
+    h->pinned_out.cap = out_bytes + out_bytes / 8;
+  }
+  char* po = (char*)h->pinned_out.p;
+  CK(cudaMemcpyAsync(po, db.lig_pos, (size_t)b.N_l * 12, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(po + (size_t)b.N_l * 12, h->dev_a14_out.p, (size_t)b.N_r * 42 * 4, cudaMemcpyDeviceToHost, st));
+  rc = check_errflag(h, st);   // synchronises the stream
+  if (rc) return rc;
+  memcpy(lig_out, po, (size_t)b.N_l * 12);
+  memcpy(atom14_out, po + (size_t)b.N_l * 12, (size_t)b.N_r * 42 * 4);
+  if (h2d_bytes) *h2d_bytes = total + (uint64_t)n_steps * SIG * 4;
+  if (d2h_bytes) *d2h_bytes = out_bytes + 4;
+  return B200_OK;
+}
+
+int b200dock_last_edge_counts(B200Handle* h, int64_t counts[5]) {
+  if (!h || !counts) return B200_ERR_INVALID;
+  for (int i = 0; i < 5; ++i) counts[i] = h->last_counts[i];
+  return B200_OK;
+}
+
+int b200dock_last_launch_count(const B200Handle* h, int64_t* n) {
+  if (!h || !n) return B200_ERR_INVALID;
+  *n = h->launches;
+  return B200_OK;
+}
+
+int b200dock_set_profiling(B200Handle* h, int enable) {
+  if (!h) return B200_ERR_INVALID;
+  h->profiling = enable != 0;
+  h->tp_events.clear(); h->event_used = 0;
+  return B200_OK;
+}
+
+int b200dock_tp_kernel_time_ms(B200Handle* h, double* ms, int64_t* launches) {
+  if (!h || !ms || !launches) return B200_ERR_INVALID;
+  double tot = 0;
+  for (auto& pr : h->tp_events) {
+    float t = 0;
+    CK(cudaEventSynchronize(pr.second));
+    CK(cudaEventElapsedTime(&t, pr.first, pr.second));
+    tot += t;
+  }
+  *ms = tot; *launches = (int64_t)h->tp_events.size();
+  h->tp_events.clear(); h->event_used = 0;
+  return B200_OK;
+}
+
+int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t cap_bytes, size_t* n_bytes) {
+  if (!h || !host_out || !n_bytes || !h->have_last) return B200_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const B200Batch& b = h->last_batch;
+  const void* src = nullptr; size_t bytes = 0;
+  if (what == B200_TAP_H_LIG) { src = h->h_lig.p; bytes = (size_t)b.N_l * HS * 4; }
+  else if (what == B200_TAP_H_ATOM) { src = h->h_atom.p; bytes = (size_t)b.N_a * HS * 4; }
+  else if (what == B200_TAP_EDGES) {
+    if (arg < 0 || arg > 5) return B200_ERR_INVALID;
+    ConvWs& w = h->cw[arg];
+    int E = 0;
+    if (w.T > 0) CK(cudaMemcpy(&E, w.seg.as<int>() + w.T, 4, cudaMemcpyDeviceToHost));
+    bytes = (size_t)E * 8;
+    if (bytes > cap_bytes) FAIL(B200_ERR_INVALID, "tap buffer too small");
+    std::vector<int> s(E), d(E);
+    if (E) { CK(cudaMemcpy(s.data(), w.es.p, (size_t)E * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(d.data(), w.ed.p, (size_t)E * 4, cudaMemcpyDeviceToHost)); }
+    int* o = (int*)host_out;
+    for (int i = 0; i < E; ++i) { o[2 * i] = s[i]; o[2 * i + 1] = d[i]; }
+    *n_bytes = bytes;
+    return B200_OK;
+  } else if (what == B200_TAP_CONV_BUF) {
+    int conv = arg / 16, which = arg % 16;
+    if (conv < 0 || conv > 5) return B200_ERR_INVALID;
+    ConvWs& w = h->cw[conv];
+    int E = 0;
+    if (w.T > 0) CK(cudaMemcpy(&E, w.seg.as<int>() + w.T, 4, cudaMemcpyDeviceToHost));
+    size_t Ep = (size_t)((E + 127) / 128) * 128;
+    if (which == 0) { src = w.emb.p; bytes = (size_t)E * NSC * 4; }
+    else if (which == 1) { src = w.sh.p; bytes = (size_t)E * (conv >= 4 ? 8 : 9) * 4; }
+    else if (which == 2) { src = w.H1.p; bytes = Ep * KP * 4; }
+    else if (which == 3) { src = w.Zt.p; bytes = Ep * w.z_max * 4; }
+    else if (which == 4) { src = w.msg.p; bytes = Ep * HS * 4; }
+    else if (which == 5) { src = w.seg.p; bytes = (size_t)(w.T + 1) * 4; }
+    else if (which == 6) { src = h->cmsg.p; bytes = (size_t)b.N_l * 12 * 4; }
+    else return B200_ERR_INVALID;
+  } else return B200_ERR_INVALID;
+  if (bytes > cap_bytes) FAIL(B200_ERR_INVALID, "tap buffer too small");
+  CK(cudaMemcpy(host_out, src, bytes, cudaMemcpyDeviceToHost));
+  *n_bytes = bytes;
+  return B200_OK;
+}
+
+int b200dock_debug_set(B200Handle* h, int key, int value) {
+  if (!h) return B200_ERR_INVALID;
+  if (key == 0) { h->debug_layers = value; return B200_OK; }
+  return B200_ERR_INVALID;
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+"""ctypes binding of ``libb200dock.so`` (include/b200dock.h) and the ``Engine`` host object.
+
+PyTorch is plumbing only: it owns device buffers, the CUDA stream and the pinned host memory
+handed to the C ABI.  If the shared library (the CUDA extension) is missing or fails to load,
+importing an ``Engine`` raises: there is no CPU or eager-PyTorch fallback on the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import batch as batch_mod
+from . import packer
+from .schedule import StepScalars
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200dock.so")
+_lib = None
+
+EXPORTS = ["b200dock_create", "b200dock_destroy", "b200dock_last_error", "b200dock_version",
+           "b200dock_load_weights", "b200dock_score", "b200dock_sample", "b200dock_sample_host",
+           "b200dock_last_edge_counts", "b200dock_last_launch_count", "b200dock_set_profiling",
+           "b200dock_tp_kernel_time_ms", "b200dock_debug_tap", "b200dock_debug_set"]
+
+
+class CCond(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("time_emb", "tr_sigma", "rot_score_norm", "tor_score_norm2",
+                                          "sc_tor_score_norm2")]
+
+
+class CStep(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("t", "dt", "tr_sigma", "rot_score_norm", "tor_score_norm2",
+                                         "sc_tor_score_norm2", "tr_g2", "tr_gs", "rot_g2", "rot_gs", "tor_g2", "tor_gs",
+                                         "sc_g2", "sc_gs")] + [("ode", C.c_int32), ("reserved", C.c_int32)]
+
+
+def load_library(path: Optional[str] = None):
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or _LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()')")
+    lib = C.CDLL(p)
+    lib.b200dock_version.restype = C.c_char_p
+    lib.b200dock_last_error.restype = C.c_char_p
+    lib.b200dock_last_error.argtypes = [C.c_void_p]
+    lib.b200dock_create.argtypes = [C.POINTER(packer.CConfig), C.c_int, C.POINTER(C.c_void_p)]
+    lib.b200dock_destroy.argtypes = [C.c_void_p]
+    lib.b200dock_destroy.restype = None
+    lib.b200dock_load_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.b200dock_score.argtypes = [C.c_void_p, C.POINTER(batch_mod.CBatch), C.POINTER(CCond)] + [C.c_void_p] * 5
+    lib.b200dock_sample.argtypes = [C.c_void_p, C.POINTER(batch_mod.CBatch), C.POINTER(CStep), C.c_int] + [C.c_void_p] * 6
+    lib.b200dock_sample_host.argtypes = [C.c_void_p, C.POINTER(batch_mod.CBatch), C.POINTER(CStep), C.c_int] + [C.c_void_p] * 4 + [
+        C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+    lib.b200dock_last_edge_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.b200dock_last_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.b200dock_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.b200dock_tp_kernel_time_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.b200dock_debug_tap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.b200dock_debug_set.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def steps_to_c(steps: Sequence[StepScalars], ode: bool = False, no_noise: bool = False):
+    """fp32 scalars exactly as the reference forms them on 0-d fp32 tensors (scFlex.py:154-205)."""
+    arr = (CStep * len(steps))()
+    f32 = np.float32
+    for i, s in enumerate(steps):
+        c = arr[i]
+        sq = np.sqrt(f32(s.dt))
+        c.t, c.dt = s.t, s.dt
+        c.tr_sigma, c.rot_score_norm = s.tr_sigma, s.rot_score_norm
+        c.tor_score_norm2, c.sc_tor_score_norm2 = s.tor_score_norm2, s.sc_tor_score_norm2
+        for name, g in (("tr", s.tr_g), ("rot", s.rot_g), ("tor", s.tor_g), ("sc", s.sc_tor_g)):
+            g = f32(g)
+            setattr(c, f"{name}_g2", float(g * g))
+            setattr(c, f"{name}_gs", float(g * sq))
+        c.ode = 1 if ode else 0
+    return arr
+
+
+def sinusoidal_embedding(t: torch.Tensor, dim: int = 32, scale: float = 1000.0) -> torch.Tensor:
+    """time_emb.py:9-26 evaluated by torch on the host (tiny; keeps sin/cos of large arguments
+    bit-identical with the reference's CPU evaluation)."""
+    import math
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float32) * -e)
+    e = (scale * t.float())[:, None] * e[None, :]
+    return torch.cat([torch.sin(e), torch.cos(e)], dim=1)
+
+
+class Engine:
+    """One handle = one device.  ``conv_kernel``: 0 SIMT fp32, 1 tcgen05 TF32x3, 2 tcgen05 TF32."""
+
+    def __init__(self, device: int = 0, conv_kernel: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("diffbindfr_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.lib = load_library()
+        self.device = device
+        self.plans = packer.Plans(conv_kernel)
+        self.h = C.c_void_p()
+        rc = self.lib.b200dock_create(C.byref(self.plans.cfg), device, C.byref(self.h))
+        self._check(rc)
+        self._keep: List[object] = []
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.b200dock_last_error(self.h).decode() if self.h else "create failed"
+            raise RuntimeError(f"b200dock error {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200dock_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
+        blob, offsets = packer.pack_state_dict(sd, prefix)
+        rc = self.lib.b200dock_load_weights(self.h, blob.ctypes.data, blob.size, offsets.ctypes.data, len(offsets))
+        self._check(rc)
+        self.n_weight_floats = int(blob.size)
+
+    # -------------------------------------------------------------------- batch
+    def upload_batch(self, batch: Dict[str, object]):
+        arrs = batch_mod.prepare(batch)
+        dev = torch.device("cuda", self.device)
+        tensors = {f: torch.from_numpy(arrs[f]).to(dev) for f in batch_mod.POINTER_FIELDS}
+        cb = batch_mod.to_struct(arrs, {f: tensors[f].data_ptr() for f in tensors})
+        return arrs, tensors, cb
+
+    # -------------------------------------------------------------------- score
+    def score(self, batch: Dict[str, object], t: torch.Tensor, tr_sigma: torch.Tensor, rot_score_norm: torch.Tensor,
+              tor_score_norm2: torch.Tensor, sc_tor_score_norm2: torch.Tensor):
+        """``TensorProductModel.forward`` on the device. ``sc_tor_score_norm2``: (N_r, 4) like set_time."""
+        arrs, tensors, cb = self.upload_batch(batch)
+        d = arrs["dims"]
+        dev = torch.device("cuda", self.device)
+        temb = sinusoidal_embedding(t.cpu()).to(dev).contiguous()
+        scm = torch.as_tensor(np.asarray(batch["sc_torsion_edge_mask"])).bool()
+        cond_t = [temb, tr_sigma.float().reshape(-1).to(dev).contiguous(), rot_score_norm.float().reshape(-1).to(dev).contiguous(),
+                  tor_score_norm2.float().reshape(-1).to(dev).contiguous() if d["n_tor"] else torch.zeros(1, device=dev),
+                  sc_tor_score_norm2.float()[scm].to(dev).contiguous() if d["n_sc"] else torch.zeros(1, device=dev)]
+        cc = CCond(*[x.data_ptr() for x in cond_t])
+        tr = torch.empty(d["B"], 3, device=dev); rot = torch.empty(d["B"], 3, device=dev)
+        tor = torch.empty(max(d["n_tor"], 1), device=dev); sc = torch.empty(max(d["n_sc"], 1), device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = self.lib.b200dock_score(self.h, C.byref(cb), C.byref(cc), tr.data_ptr(), rot.data_ptr(), tor.data_ptr(),
+                                     sc.data_ptr(), st)
+        self._check(rc)
+        self._keep = [tensors, cond_t]
+        return tr, rot, tor[:d["n_tor"]], sc[:d["n_sc"]]
+
+    # ------------------------------------------------------------------- sample
+    @staticmethod
+    def pack_noise(noise: Sequence[Dict[str, torch.Tensor]]) -> torch.Tensor:
+        rows = [torch.cat([z["tr"].reshape(-1), z["rot"].reshape(-1), z["tor"].reshape(-1), z["sc"].reshape(-1)]).float()
+                for z in noise]
+        return torch.stack(rows).contiguous()
+
+    def sample_device(self, batch: Dict[str, object], steps: Sequence[StepScalars], noise: torch.Tensor,
+                      trajectory: bool = False, ode: bool = False):
+        """Inputs uploaded first; only the device sampling is inside the C call (``value`` timing)."""
+        arrs, tensors, cb = self.upload_batch(batch)
+        d = arrs["dims"]
+        dev = torch.device("cuda", self.device)
+        n = len(steps)
+        csteps = steps_to_c(steps, ode)
+        temb = sinusoidal_embedding(torch.tensor([s.t for s in steps], dtype=torch.float32)).contiguous()
+        noise_d = noise.to(dev).contiguous()
+        lig_traj = torch.empty(n, d["N_l"], 3, device=dev) if trajectory else None
+        a14 = torch.empty(d["N_r"], 14, 3, device=dev)
+        a14_traj = torch.empty(n, d["N_r"], 14, 3, device=dev) if trajectory else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        state = dict(cb=cb, csteps=csteps, temb=temb, noise=noise_d, lig_traj=lig_traj, a14=a14, a14_traj=a14_traj,
+                     tensors=tensors, n=n, stream=st, dims=d)
+        self._keep = [state]
+        return state
+
+    def run_sample(self, state) -> None:
+        rc = self.lib.b200dock_sample(
+            self.h, C.byref(state["cb"]), state["csteps"], state["n"], state["temb"].data_ptr(), state["noise"].data_ptr(),
+            state["lig_traj"].data_ptr() if state["lig_traj"] is not None else None, state["a14"].data_ptr(),
+            state["a14_traj"].data_ptr() if state["a14_traj"] is not None else None, state["stream"])
+        self._check(rc)
+
+    def sample(self, batch, steps, noise, trajectory=False, ode=False):
+        state = self.sample_device(batch, steps, noise, trajectory, ode)
+        self.run_sample(state)
+        return state["tensors"]["lig_pos"], state["a14"], state["lig_traj"], state["a14_traj"]
+
+    def sample_host(self, arrs: Dict[str, object], steps: Sequence[StepScalars], noise: torch.Tensor, ode: bool = False):
+        """End-to-end call with HOST buffers (prepared by ``batch.prepare``): H2D, 20 steps, D2H inside."""
+        d = arrs["dims"]
+        cb = batch_mod.to_struct(arrs, {f: arrs[f].ctypes.data for f in batch_mod.POINTER_FIELDS})
+        csteps = steps_to_c(steps, ode)
+        temb = sinusoidal_embedding(torch.tensor([s.t for s in steps], dtype=torch.float32)).contiguous()
+        noise = noise.contiguous()
+        lig = np.empty((d["N_l"], 3), dtype=np.float32)
+        a14 = np.empty((d["N_r"], 14, 3), dtype=np.float32)
+        h2d, d2h = C.c_uint64(0), C.c_uint64(0)
+        st = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+        rc = self.lib.b200dock_sample_host(self.h, C.byref(cb), csteps, len(steps), temb.data_ptr(), noise.data_ptr(),
+                                           lig.ctypes.data, a14.ctypes.data, C.byref(h2d), C.byref(d2h), st)
+        self._check(rc)
+        return torch.from_numpy(lig), torch.from_numpy(a14), int(h2d.value), int(d2h.value)
+
+    # ------------------------------------------------------------ introspection
+    def edge_counts(self) -> Dict[str, int]:
+        a = (C.c_int64 * 5)()
+        self._check(self.lib.b200dock_last_edge_counts(self.h, a))
+        return dict(zip(["lig", "atom", "cross", "tor", "sc"], [int(x) for x in a]))
+
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        self._check(self.lib.b200dock_last_launch_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.b200dock_set_profiling(self.h, 1 if on else 0))
+
+    def tp_kernel_time_ms(self) -> Tuple[float, int]:
+        ms, n = C.c_double(0), C.c_int64(0)
+        self._check(self.lib.b200dock_tp_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def debug_set(self, key: int, value: int):
+        self._check(self.lib.b200dock_debug_set(self.h, key, value))
+
+    def tap(self, what: int, arg: int = 0, dtype=np.float32, max_bytes: int = 1 << 30) -> np.ndarray:
+        buf = np.empty(min(max_bytes, 1 << 28), dtype=np.uint8)
+        n = C.c_size_t(0)
+        self._check(self.lib.b200dock_debug_tap(self.h, what, arg, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf[:n.value].view(dtype).copy()

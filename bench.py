@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffBindFR reverse-diffusion hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (libb200dock through the C ABI)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: oracle port of the reference path
+
+One "step" = one reverse-SDE denoising step of a 40-pose batch (score network + SDE perturbation +
+ligand pose update + side-chain rebuild + graph rebuild), workload cfg-A = BASELINE.json configs[1].
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is derived.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from diffbindfr_b200 import schedule, spec, synth, weights  # noqa: E402
+
+METRIC = "denoising-steps/sec (40-pose batch)"
+UNIT = "steps/s"
+
+
+def workload_kwargs(name):
+    return dict(synth.WORKLOADS[name])
+
+
+def cycle_steps(n):
+    sch = schedule.make_schedule()
+    out = []
+    for i in range(n):
+        s = sch[i % len(sch)]
+        out.append(s)
+    return out
+
+
+def noise_for(b, n, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    B, n_tor, n_sc = b["num_graphs"], int(b["tor_edge_mask"].sum()), int(b["sc_torsion_edge_mask"].sum())
+    return torch.randn(n, 6 * B + n_tor + n_sc, generator=g)
+
+
+def tp_flops(edge_counts):
+    """Algorithmic FLOPs of the tensor-product contraction kernel for one step:
+    per edge 2*144*W (weight generator, layer 2) + W (bias) + T (fold with the CG-contracted features)."""
+    tot = 0
+    conv_edges = edge_counts["lig"] + edge_counts["atom"] + 2 * edge_counts["cross"]
+    for l in range(6):
+        tp = spec.conv_tp(l)
+        T = 2 * sum(p.numel * p.k3 for p in tp.paths)
+        tot += conv_edges * (2 * 144 * tp.weight_numel + tp.weight_numel + T)
+    tp = spec.tor_tp()
+    T = 2 * sum(p.numel * p.k3 for p in tp.paths)
+    tot += (edge_counts["tor"] + edge_counts["sc"]) * (2 * 144 * tp.weight_numel + tp.weight_numel + T)
+    return tot
+
+
+def step_flops(edge_counts, n_lig):
+    """Whole-step algorithmic FLOPs: adds the first FC layer and the centre conv."""
+    conv_edges = edge_counts["lig"] + edge_counts["atom"] + 2 * edge_counts["cross"]
+    extra = 6 * conv_edges * 2 * 144 * 144 + (edge_counts["tor"] + edge_counts["sc"]) * 2 * 144 * 144
+    extra += n_lig * 2 * 96 * (96 + 336)
+    return tp_flops(edge_counts) + extra
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+def cpu_baseline(n_poses=1, steps=1, threads=None, seed=0):
+    """Oracle port of the reference path timed on the host cores on a bounded sample of cfg-A:
+    ``n_poses`` of the 40 poses for ``steps`` full denoising steps; scaled to the 40-pose step."""
+    from oracle import sampler as osampler
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    kw = workload_kwargs("cfgA"); kw["n_poses"] = n_poses
+    b = synth.make_batch(**kw, seed=seed)
+    sd = weights.random_state_dict(0)
+    sch = schedule.make_schedule()
+    norm = {round(s.rot_sigma, 9): s for s in sch}
+    rot_fn = lambda x: min(sch, key=lambda s: abs(s.rot_sigma - x)).rot_score_norm
+    tor_fn = lambda x: min(sch, key=lambda s: abs(s.sc_tor_sigma - x)).tor_score_norm2
+    cfg = dict(osampler.CFG); cfg["actual_steps"] = steps
+    torch.manual_seed(1)
+    t0 = time.perf_counter()
+    osampler.sample(sd, b, cfg=cfg, rot_norm_fn=rot_fn, tor_norm_fn=tor_fn)
+    dt = time.perf_counter() - t0
+    per_40pose_step = dt / steps * (40.0 / n_poses)
+    return dict(value=1.0 / per_40pose_step, unit=UNIT, cores=threads, kind="port",
+                sample=f"{n_poses} of 40 cfg-A poses x {steps} full denoising step(s) through oracle/sampler.py "
+                       f"(fp32, torch CPU kernels, {threads} threads), {dt:.1f} s, scaled x{40 // n_poses} to the 40-pose step")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    n_poses = 1
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(n_poses=n_poses, steps=1, seed=i)
+        if i >= args.warmup:
+            times.append(1.0 / r["value"])
+        last = r
+    ms = float(np.mean(times)) * 1e3
+    val = 1e3 / ms
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "cfgA: 1 complex x 40 poses x 36 residues (~300 pocket atoms) x 30 ligand atoms; "
+                                   "each timed step = 1 of the 40 poses through one full denoising step, scaled x40"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfgA")
+    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-poses", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    from diffbindfr_b200 import batch as batch_mod
+    from diffbindfr_b200.engine import Engine
+
+    # weak scaling: every rank owns one 40-pose batch (poses / complexes shard without any exchange)
+    b = synth.make_batch(**workload_kwargs(args.workload), seed=rank)
+    sd = weights.random_state_dict(0)
+    eng = Engine(local, conv_kernel=args.conv_kernel)
+    eng.load_state_dict(sd)
+    K, W = args.steps, max(args.warmup, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ("value")
+    if W:
+        st = eng.sample_device(b, cycle_steps(W), noise_for(b, W, 7))
+        eng.run_sample(st)
+    state = eng.sample_device(b, cycle_steps(K), noise_for(b, K, 1))
+    eng.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0.record()
+    eng.run_sample(state)
+    if dist is not None:   # the job's only collective: gather the final ligand coordinates of every rank
+        out = [torch.empty_like(state["tensors"]["lig_pos"]) for _ in range(world)]
+        dist.all_gather(out, state["tensors"]["lig_pos"])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if clocks else None
+    tp_ms, tp_launches = eng.tp_kernel_time_ms()
+    eng.set_profiling(False)
+    launches = eng.launch_count()
+    counts = eng.edge_counts()
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = world * 1e3 / ms_step
+
+    # ---- end to end through the host-buffer C-ABI call ("e2e")
+    arrs = batch_mod.prepare(b)
+    zn = noise_for(b, K, 1)
+    eng.sample_host(arrs, cycle_steps(min(W, 2) or 1), noise_for(b, min(W, 2) or 1, 3))
+    barrier()
+    t0 = time.perf_counter()
+    lig_h, a14_h, h2d, d2h = eng.sample_host(arrs, cycle_steps(K), zn)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * K / float(te.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    # last step's edge counts stand in for all K steps (they drift by <1 % as poses move)
+    f_tp = tp_flops(counts)
+    achieved = f_tp * K / (tp_ms * 1e-3) / 1e12 if tp_ms > 0 else None
+    kname = {0: "k_conv_tp_simt (fp32 SIMT)", 1: "k_conv_tp_tc (tcgen05 TF32x3)", 2: "k_conv_tp_tc (tcgen05 TF32)"}[args.conv_kernel]
+    roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+            "kernel": kname, "kernel_ms_per_step": tp_ms / K, "kernel_share_of_step": tp_ms / ms_total,
+            "launches_per_step": tp_launches / K, "algorithmic_flops_per_step": f_tp, "peak_source": peak_src}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline(n_poses=args.cpu_baseline_poses, steps=1)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {0: "f32", 1: "tf32x3", 2: "tf32"}[args.conv_kernel], "data": "synthetic",
+            "config": {"workload": f"{args.workload}: 1 complex x 40 poses x 36 residues (~300 pocket atoms) x 30 ligand atoms per GPU"
+                       if args.workload == "cfgA" else args.workload,
+                       "poses_per_gpu": int(b["num_graphs"]), "pocket_atoms": int(b["rec_atm_pos"].shape[0]),
+                       "ligand_atoms": int(b["lig_pos"].shape[0]), "edges": counts, "conv_kernel": args.conv_kernel,
+                       "random_init_weights": True, "parallelism": f"pose-sharded x{world}, one final all_gather",
+                       "l2": "no explicit flush: the per-step working set (per-edge H1/Z/message buffers "
+                             f"~{(counts['lig'] + counts['atom'] + 2 * counts['cross']) * (160 + 624 + 168) * 4 / 1e9:.2f} GB + 101 MB weights) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                    "note": "b200dock_sample_host: pageable host arrays -> pinned arena -> H2D, K steps, D2H of final coordinates"},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "step_algorithmic_tflop": step_flops(counts, int(b["lig_pos"].shape[0])) / 1e12}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

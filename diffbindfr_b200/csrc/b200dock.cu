@@ -33,11 +33,12 @@ struct Buf {
 
 struct ConvWs {                 // per edge family: lig, atom, al, la, tor, sc
   int T = 0; int cap = 0; int z_max = 0;
-  Buf counts, seg, es, ed, eaux, emb, sh, H1, Zt, msg;
+  Buf counts, seg, es, ed, eaux, emb, sh, H1, H1lo, Zt, msg;
 };
 
 struct ConvW {                  // views into the device weight blob
   const float *W1t, *b1, *W2p; LnParams ln;
+  const float *W2hi = nullptr, *W2lo = nullptr; int n_cols = 0;
 };
 
 }  // namespace
@@ -50,7 +51,7 @@ struct B200Handle {
   DevPlan dplans[B200_N_PLANS];
   std::vector<void*> plan_allocs;
   int* d_tor_cg_ijk = nullptr; float* d_tor_cg_val = nullptr;
-  float* d_blob = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
+  float* d_blob = nullptr; float* d_w2split = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
   ConvW convw[26];
   // workspace
   ConvWs cw[6];
@@ -125,7 +126,9 @@ int setup_workspace(B200Handle* h, const B200Batch& b) {
     ENS(w.es, (size_t)w.cap * 4); ENS(w.ed, (size_t)w.cap * 4);
     if (c == 0) ENS(w.eaux, (size_t)w.cap * 4);
     ENS(w.emb, (size_t)w.cap * NSC * 4); ENS(w.sh, (size_t)w.cap * 9 * 4);
-    ENS(w.H1, (size_t)w.cap * KP * 4); ENS(w.Zt, (size_t)w.cap * w.z_max * 4); ENS(w.msg, (size_t)w.cap * HS * 4);
+    ENS(w.H1, (size_t)w.cap * KP * 4);
+    if (h->cfg.conv_kernel == 1) ENS(w.H1lo, (size_t)w.cap * KP * 4);
+    ENS(w.Zt, (size_t)w.cap * w.z_max * 4); ENS(w.msg, (size_t)w.cap * HS * 4);
   }
   for (int m = 0; m < 6; ++m) ENS(h->pre[m], (size_t)b.B * NSC * 4);
   ENS(h->h_lig, (size_t)b.N_l * HS * 4); ENS(h->h_atom, (size_t)b.N_a * HS * 4);
@@ -138,6 +141,16 @@ int setup_workspace(B200Handle* h, const B200Batch& b) {
   ENS(h->c_temb, (size_t)b.B * SIG * 4); ENS(h->c_trs, (size_t)b.B * 4); ENS(h->c_rotn, (size_t)b.B * 4);
   ENS(h->c_torn, (size_t)(b.n_tor + 1) * 4); ENS(h->c_scn, (size_t)(b.n_sc + 1) * 4);
   return B200_OK;
+}
+
+__global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = src[i];
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    float h = __uint_as_float(hb);
+    hi[i] = h; lo[i] = v - h;
+  }
 }
 
 EdgeMlp edge_mlp(const B200Handle* h, int section, int n_bond, int n_sigma) {
@@ -176,29 +189,33 @@ void edge_feat(B200Handle* h, const B200Batch& b, ConvWs& w, EdgeMlp mlp, const 
   h->launches += 1;
 }
 
-int launch_tp(B200Handle* h, const ConvLaunch& L, cudaStream_t st) {
+int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t st) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
   if (h->cfg.conv_kernel == 0) {
     k_conv_tp_simt<<<h->n_sms, TP_THREADS, TP_SMEM, st>>>(L);
   } else {
-    rc = launch_conv_tc(L, h->cfg.conv_kernel, h->n_sms, st);
+    rc = launch_conv_tc(L, X, h->cfg.conv_kernel, h->n_sms, st);
   }
   if (h->profiling) { cudaEventRecord(e1, st); h->tp_events.push_back({e0, e1}); }
   h->launches += 1;
-  if (rc) FAIL(B200_ERR_CUDA, "tcgen05 conv launch failed");
+  if (rc) { char m[64]; snprintf(m, sizeof m, "tcgen05 conv launch failed (%d)", rc); FAIL(B200_ERR_CUDA, m); }
   return B200_OK;
 }
 
 ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* tabA, const float* tabB, int mode,
-                   const int* bonds, int sh_stride) {
+                   const int* bonds, int sh_stride, TcExtra& X, int slot) {
   ConvArgs C{};
+  X.H1_lo[slot] = w.H1lo.as<float>(); X.W2_lo[slot] = h->convw[widx].W2lo;
+  X.h1_rows[slot] = (uint64_t)w.cap; X.w2_rows[slot] = (uint64_t)h->convw[widx].n_cols;
   C.n_edges = w.seg.as<int>() + w.T; C.es = w.es.as<int>(); C.ed = w.ed.as<int>();
   C.emb = w.emb.as<float>(); C.sh = w.sh.as<float>(); C.sh_stride = sh_stride;
   C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode; C.plan = plan;
-  C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1; C.W2p = h->convw[widx].W2p;
-  C.H1 = w.H1.as<float>(); C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
+  C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1;
+  C.W2p = (h->cfg.conv_kernel == 1) ? h->convw[widx].W2hi : h->convw[widx].W2p;
+  C.H1 = w.H1.as<float>(); C.H1_lo = (h->cfg.conv_kernel == 1) ? w.H1lo.as<float>() : nullptr;
+  C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
   return C;
 }
 
@@ -254,14 +271,15 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
   for (int l = 0; l < h->debug_layers; ++l) {
     const int plan = plan_of_layer(l);
     ConvLaunch L{};
+    TcExtra X{};
     L.n = 4;
-    L.c[0] = conv_args(h, h->cw[0], 0 * 6 + l, plan, hl, hl, 0, nullptr, 9);     // lig
-    L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9);     // atom
-    L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9);     // al: target lig, gather atom
-    L.c[3] = conv_args(h, h->cw[3], 3 * 6 + l, plan, ha, hl, 0, nullptr, 9);     // la: target atom, gather lig
+    L.c[0] = conv_args(h, h->cw[0], 0 * 6 + l, plan, hl, hl, 0, nullptr, 9, X, 0);     // lig
+    L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9, X, 1);     // atom
+    L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9, X, 2);     // al: target lig, gather atom
+    L.c[3] = conv_args(h, h->cw[3], 3 * 6 + l, plan, ha, hl, 0, nullptr, 9, X, 3);     // la: target atom, gather lig
     k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
     h->launches += 1;
-    if ((rc = launch_tp(h, L, st))) return rc;
+    if ((rc = launch_tp(h, L, X, st))) return rc;
     NodeUpdateArgs U{};
     U.plan = plan;
     U.N = b.N_l; U.h = hl;
@@ -299,11 +317,12 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     else edge_feat<G_SC>(h, b, w, edge_mlp(h, B200_W_SC_EDGE, 0, 0), nullptr, 4.0f, st);
     const float* tab = which == 0 ? hl : ha;
     ConvLaunch L{};
+    TcExtra X{};
     L.n = 1;
-    L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8);
+    L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8, X, 0);
     k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
     h->launches += 1;
-    if ((rc = launch_tp(h, L, st))) return rc;
+    if ((rc = launch_tp(h, L, X, st))) return rc;
     TorHeadArgs T{};
     T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
     T.mlp = W + off[which == 0 ? B200_W_TOR_FINAL : B200_W_SC_FINAL];
@@ -442,7 +461,7 @@ void b200dock_destroy(B200Handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   auto fr = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
-  for (auto& w : h->cw) { fr(w.counts); fr(w.seg); fr(w.es); fr(w.ed); fr(w.eaux); fr(w.emb); fr(w.sh); fr(w.H1); fr(w.Zt); fr(w.msg); }
+  for (auto& w : h->cw) { fr(w.counts); fr(w.seg); fr(w.es); fr(w.ed); fr(w.eaux); fr(w.emb); fr(w.sh); fr(w.H1); fr(w.H1lo); fr(w.Zt); fr(w.msg); }
   for (auto& b : h->pre) fr(b);
   Buf* all[] = {&h->h_lig, &h->h_atom, &h->jmax_lig, &h->jmax_atom, &h->centre, &h->cmsg, &h->s_tr, &h->s_rot, &h->s_tor,
                 &h->s_sc, &h->atom14, &h->errflag, &h->c_temb, &h->c_trs, &h->c_rotn, &h->c_torn, &h->c_scn,
@@ -452,6 +471,7 @@ void b200dock_destroy(B200Handle* h) {
   if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
   for (void* p : h->plan_allocs) cudaFree(p);
   if (h->d_blob) cudaFree(h->d_blob);
+  if (h->d_w2split) cudaFree(h->d_w2split);
   for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -480,6 +500,22 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     w.ln.bias = r; r += nsc;
     if ((size_t)(r - h->d_blob) > n) FAIL(B200_ERR_INVALID, "weight blob too small for its section table");
     if (((uintptr_t)w.W2p & 15) != 0) FAIL(B200_ERR_INVALID, "conv record is not 16-byte aligned");
+    w.n_cols = P.n_cols;
+  }
+  if (h->cfg.conv_kernel == 1) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
+    size_t tot = 0;
+    for (int i = 0; i < 26; ++i) tot += (size_t)h->convw[i].n_cols * KP;
+    if (h->d_w2split) CK(cudaFree(h->d_w2split));
+    CK(cudaMalloc((void**)&h->d_w2split, 2 * tot * sizeof(float) + 1024));
+    size_t pos = 0;
+    for (int i = 0; i < 26; ++i) {
+      size_t n = (size_t)h->convw[i].n_cols * KP;
+      float* hi = h->d_w2split + pos; float* lo = h->d_w2split + tot + pos;
+      k_split_tf32<<<148 * 4, 256>>>(h->convw[i].W2p, n, hi, lo);
+      h->convw[i].W2hi = hi; h->convw[i].W2lo = lo;
+      pos += n;
+    }
+    CK(cudaDeviceSynchronize());
   }
   h->weights = true;
   return B200_OK;

@@ -27,6 +27,7 @@ struct ConvArgs {
   const float* W1t; const float* b1;   // [144][144] ([in][out]), [144]
   const float* W2p;         // [n_cols][160]
   float* H1;                // [E_pad][160]
+  float* H1_lo;             // optional: H1 - tf32(H1) for the 3xTF32 tensor-core mode (H1 then holds tf32(H1))
   float* Zt;                // [tiles][z_numel][128]
   float* msg;               // [E_pad][HS]
 };
@@ -116,13 +117,22 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float v = fmaxf(acc[i][j] + bj, 0.0f);
-            C.H1[(size_t)(e0 + eg * 8 + i) * KP + jg * 9 + j] = v;
+            const size_t o = (size_t)(e0 + eg * 8 + i) * KP + jg * 9 + j;
+            if (C.H1_lo) {
+              uint32_t hb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+              float hi = __uint_as_float(hb);
+              C.H1[o] = hi; C.H1_lo[o] = v - hi;
+            } else {
+              C.H1[o] = v;
+            }
           }
         }
         // bias column and zero padding
         for (int idx = tid; idx < TILE_E * 16; idx += PRO_THREADS) {
           int e = idx >> 4, c = idx & 15;
           C.H1[(size_t)(e0 + e) * KP + 144 + c] = (c == 0) ? 1.0f : 0.0f;
+          if (C.H1_lo) C.H1_lo[(size_t)(e0 + e) * KP + 144 + c] = 0.0f;
         }
       }
       // ---- Z: thread = (edge lane, half); rows (path, u) strided over the two halves

@@ -69,9 +69,11 @@ def plan_specs() -> List[spec.TPSpec]:
 
 
 def chunks_of(tp: spec.TPSpec) -> List[Tuple[int, int, int]]:
-    """(first column, n columns, path index): whole-u slices of one path, at most 192 columns."""
+    """(first column, n columns, path index): whole-u slices of one path, at most 192 columns, ordered so
+    that all chunks feeding one output irreps block are consecutive (the tensor-core epilogue keeps that
+    block in registers and stores it once)."""
     out = []
-    for pi, p in enumerate(tp.paths):
+    for pi, p in sorted(enumerate(tp.paths), key=lambda t: (t[1].out_off, t[0])):   # grouped by output block
         upc = max(CHUNK_COLS // p.mulo, 1)
         for u0 in range(0, p.mul1, upc):
             nu = min(upc, p.mul1 - u0)

@@ -2,6 +2,7 @@
 // declared in include/b200dock.h.  Everything is launched on the caller's stream with fixed-size
 // grids that read their extents from device memory, so one evaluation needs no host round trip.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -67,6 +68,7 @@ struct B200Handle {
   B200Batch last_batch; bool have_last = false;
   int n_sms = 148;
   int debug_layers = 6;
+  int tp_grid = 148;
 };
 
 namespace {
@@ -196,7 +198,7 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t
   if (h->cfg.conv_kernel == 0) {
     k_conv_tp_simt<<<h->n_sms, TP_THREADS, TP_SMEM, st>>>(L);
   } else {
-    rc = launch_conv_tc(L, X, h->cfg.conv_kernel, h->n_sms, st);
+    rc = launch_conv_tc(L, X, h->cfg.conv_kernel, h->tp_grid, st);
   }
   if (h->profiling) { cudaEventRecord(e1, st); h->tp_events.push_back({e0, e1}); }
   h->launches += 1;
@@ -213,7 +215,7 @@ ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* ta
   C.emb = w.emb.as<float>(); C.sh = w.sh.as<float>(); C.sh_stride = sh_stride;
   C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode; C.plan = plan;
   C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1;
-  C.W2p = (h->cfg.conv_kernel == 1) ? h->convw[widx].W2hi : h->convw[widx].W2p;
+  C.W2p = (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3) ? h->convw[widx].W2hi : h->convw[widx].W2p;
   C.H1 = w.H1.as<float>(); C.H1_lo = (h->cfg.conv_kernel == 1) ? w.H1lo.as<float>() : nullptr;
   C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
   return C;
@@ -422,6 +424,8 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->n_sms = prop.multiProcessorCount;
+  h->tp_grid = h->n_sms;
+  if (const char* g = getenv("B200DOCK_TP_GRID")) { int v = atoi(g); if (v > 0 && v <= h->n_sms) h->tp_grid = v; }
   for (int p = 0; p < B200_N_PLANS; ++p) {
     const B200ConvPlan& s = cfg->plans[p];
     DevPlan& d = h->dplans[p];
@@ -446,6 +450,21 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
     h->hold_i.emplace_back(s.chunk_path, s.chunk_path + s.n_chunks);
   }
   CK(cudaMemcpyToSymbol(c_plans, h->dplans, sizeof(DevPlan) * B200_N_PLANS));
+  {
+    std::vector<float> dense((size_t)B200_N_PLANS * B200_MAX_PATHS * 45, 0.0f);
+    for (int p = 0; p < B200_N_PLANS; ++p) {
+      const B200ConvPlan& s = cfg->plans[p];
+      for (int q = 0; q < s.n_paths; ++q) {
+        const B200Path& pa = s.paths[q];
+        for (int c = pa.cg_off; c < pa.cg_off + pa.cg_n; ++c) {
+          int ijk = s.cg_ijk[c];
+          int i = ijk & 255, j = (ijk >> 8) & 255, k = (ijk >> 16) & 255;
+          if (i < 3 && j < 5 && k < 3) dense[((size_t)p * B200_MAX_PATHS + q) * 45 + (i * 5 + j) * 3 + k] = s.cg_val[c];
+        }
+      }
+    }
+    CK(cudaMemcpyToSymbol(c_cg_dense, dense.data(), dense.size() * sizeof(float)));
+  }
   CK(cudaMemcpyToSymbol(c_atom14_group, cfg->atom14_group, sizeof(int) * 21 * 14));
   int rc;
   if ((rc = upload(h, cfg->tor_cg_ijk, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_ijk))) return rc;
@@ -502,7 +521,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     if (((uintptr_t)w.W2p & 15) != 0) FAIL(B200_ERR_INVALID, "conv record is not 16-byte aligned");
     w.n_cols = P.n_cols;
   }
-  if (h->cfg.conv_kernel == 1) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
+  if (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
     size_t tot = 0;
     for (int i = 0; i < 26; ++i) tot += (size_t)h->convw[i].n_cols * KP;
     if (h->d_w2split) CK(cudaFree(h->d_w2split));

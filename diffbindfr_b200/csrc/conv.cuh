@@ -13,6 +13,36 @@
 #include "common.cuh"
 
 __constant__ DevPlan c_plans[B200_N_PLANS];
+// dense Clebsch-Gordan blocks per (plan, path): C[i][j][k] with i<3 (in1), j<5 (sh), k<3 (out), zero padded
+__constant__ float c_cg_dense[B200_N_PLANS][B200_MAX_PATHS][45];
+
+// Z_p[u][k] = sum_i x1[u][i] * M[i][k],  M[i][k] = sum_j C[i][j][k] sh[j]  (M once per (edge, path))
+template <int D1, int K3>
+__device__ __forceinline__ void z_path(const float* __restrict__ cg, const float* __restrict__ shv, int d2,
+                                       const float* __restrict__ x1, int U, int u0, int ustep,
+                                       float* __restrict__ out /* + z_off*128 + e */) {
+  float M[D1][K3];
+#pragma unroll
+  for (int i = 0; i < D1; ++i)
+#pragma unroll
+    for (int k = 0; k < K3; ++k) {
+      float m = 0.0f;
+      for (int j = 0; j < d2; ++j) m = fmaf(cg[(i * 5 + j) * 3 + k], shv[j], m);
+      M[i][k] = m;
+    }
+  for (int u = u0; u < U; u += ustep) {
+    float x[D1];
+#pragma unroll
+    for (int i = 0; i < D1; ++i) x[i] = x1[u * D1 + i];
+#pragma unroll
+    for (int k = 0; k < K3; ++k) {
+      float z = 0.0f;
+#pragma unroll
+      for (int i = 0; i < D1; ++i) z = fmaf(x[i], M[i][k], z);
+      out[(size_t)(u * K3 + k) * TILE_E] = z;
+    }
+  }
+}
 
 struct ConvArgs {
   const int* n_edges;       // device scalar
@@ -35,14 +65,21 @@ struct ConvLaunch { ConvArgs c[4]; int n; };
 
 #define PRO_THREADS 256
 #define PRO_XS_STRIDE 132    // floats per k-row of the transposed edge-input tile (128 + pad, 16B aligned)
-constexpr size_t PRO_SMEM = (size_t)(144 * PRO_XS_STRIDE + 144 * 144 + 9 * 128 + 3 * 128) * 4;
+#define PRO_HS_STRIDE 161    // staged H1 rows
+#define PRO_X1_STRIDE 169    // staged gathered node rows (odd: conflict-free per-edge access)
+#define PRO_U_FLOATS (128 * PRO_X1_STRIDE)   // union region: Xs (144x132) / H1 stage (128x161) / x1 stage (128x169)
+constexpr size_t PRO_SMEM = (size_t)(PRO_U_FLOATS + 144 * 144 + 9 * 128 + 2 * 128) * 4;
 
+// Per 128-edge tile: (1) gather xin = [edge_emb | hA[:48] | hB[:48]] transposed into shared memory,
+// (2) H1 = relu(W1 xin + b1) with an 8x9 register tile per thread, staged through shared memory so the
+// 640-byte H1 rows leave coalesced (optionally split into TF32 hi/lo), (3) gather the x1 node rows
+// coalesced into shared memory and contract them with the edge harmonics through the sparse CG tables.
 __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) {
   extern __shared__ float smem[];
-  float* Xs = smem;                                  // [144][132]   xin, k-major
-  float* W1s = Xs + 144 * PRO_XS_STRIDE;             // [144][144]   W1t
+  float* U = smem;                                   // union region
+  float* W1s = U + PRO_U_FLOATS;                     // [144][144]   W1t
   float* Ss = W1s + 144 * 144;                       // [9][128]     edge harmonics
-  int* Is = reinterpret_cast<int*>(Ss + 9 * 128);    // [3][128]     s, d, (unused)
+  int* Is = reinterpret_cast<int*>(Ss + 9 * 128);    // [2][128]     s, d
   const int tid = threadIdx.x;
   int tiles_before = 0;
   for (int ci = 0; ci < L.n; ++ci) {
@@ -53,6 +90,7 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
     int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
     tiles_before += ntile;
     if (first >= ntile) continue;
+    __syncthreads();
     for (int i = tid; i < 144 * 144; i += PRO_THREADS) W1s[i] = C.W1t[i];
     for (int tile = first; tile < ntile; tile += gridDim.x) {
       const int e0 = tile * TILE_E;
@@ -62,7 +100,8 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
         Is[128 + tid] = C.ed[e0 + tid];
       }
       __syncthreads();
-      // ---- gather xin (transposed into Xs[k][e]) and the edge harmonics
+      // ---- (1) gather xin (transposed into Xs[k][e]) and the edge harmonics
+      float* Xs = U;
       for (int idx = tid; idx < TILE_E * 36; idx += PRO_THREADS) {   // 36 float4 per edge
         int e = idx / 36, q = idx % 36;
         float4 v;
@@ -91,7 +130,7 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
         Ss[j * 128 + e] = (j < C.sh_stride) ? C.sh[(size_t)(e0 + e) * C.sh_stride + j] : 0.0f;
       }
       __syncthreads();
-      // ---- H1 = relu(W1 xin + b1): thread tile 8 edges x 9 outputs
+      // ---- (2) H1 = relu(W1 xin + b1): thread tile 8 edges x 9 outputs
       {
         const int eg = tid & 15, jg = tid >> 4;
         float acc[8][9];
@@ -99,6 +138,7 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 9; ++j) acc[i][j] = 0.0f;
+#pragma unroll 2
         for (int k = 0; k < 144; ++k) {
           float4 a0 = *reinterpret_cast<const float4*>(Xs + k * PRO_XS_STRIDE + eg * 8);
           float4 a1 = *reinterpret_cast<const float4*>(Xs + k * PRO_XS_STRIDE + eg * 8 + 4);
@@ -111,54 +151,66 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
 #pragma unroll
             for (int j = 0; j < 9; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
+        __syncthreads();                               // everyone is done reading Xs
+        float* Hst = U;                                // [128][161]
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
           float bj = C.b1[jg * 9 + j];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v = fmaxf(acc[i][j] + bj, 0.0f);
-            const size_t o = (size_t)(e0 + eg * 8 + i) * KP + jg * 9 + j;
-            if (C.H1_lo) {
-              uint32_t hb;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-              float hi = __uint_as_float(hb);
-              C.H1[o] = hi; C.H1_lo[o] = v - hi;
-            } else {
-              C.H1[o] = v;
-            }
+          for (int i = 0; i < 8; ++i) Hst[(eg * 8 + i) * PRO_HS_STRIDE + jg * 9 + j] = fmaxf(acc[i][j] + bj, 0.0f);
+        }
+        for (int idx = tid; idx < TILE_E * 16; idx += PRO_THREADS) {   // bias column and zero padding
+          int e = idx >> 4, c = idx & 15;
+          Hst[e * PRO_HS_STRIDE + 144 + c] = (c == 0) ? 1.0f : 0.0f;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < TILE_E * (KP / 4); idx += PRO_THREADS) {   // coalesced 640-byte rows
+          int e = idx / (KP / 4), q = idx % (KP / 4);
+          const float* src = Hst + e * PRO_HS_STRIDE + q * 4;
+          float4 v = make_float4(src[0], src[1], src[2], src[3]);
+          const size_t o = (size_t)(e0 + e) * KP + q * 4;
+          if (C.H1_lo) {
+            float4 hi, lo;
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb); lo.x = v.x - hi.x;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb); lo.y = v.y - hi.y;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb); lo.z = v.z - hi.z;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb); lo.w = v.w - hi.w;
+            *reinterpret_cast<float4*>(C.H1 + o) = hi;
+            *reinterpret_cast<float4*>(C.H1_lo + o) = lo;
+          } else {
+            *reinterpret_cast<float4*>(C.H1 + o) = v;
           }
         }
-        // bias column and zero padding
-        for (int idx = tid; idx < TILE_E * 16; idx += PRO_THREADS) {
-          int e = idx >> 4, c = idx & 15;
-          C.H1[(size_t)(e0 + e) * KP + 144 + c] = (c == 0) ? 1.0f : 0.0f;
-          if (C.H1_lo) C.H1_lo[(size_t)(e0 + e) * KP + 144 + c] = 0.0f;
-        }
       }
-      // ---- Z: thread = (edge lane, half); rows (path, u) strided over the two halves
+      __syncthreads();
+      // ---- (3) x1 rows -> shared (coalesced), then Z
       {
+        float* X1 = U;                                 // [128][169]
+        const int nq = (P.in_dim + 3) / 4;
+        for (int idx = tid; idx < TILE_E * nq; idx += PRO_THREADS) {
+          int e = idx / nq, q = idx % nq;
+          float4 v = *reinterpret_cast<const float4*>(C.tabB + (size_t)Is[128 + e] * HS + q * 4);
+          float* o = X1 + e * PRO_X1_STRIDE + q * 4;
+          o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+        __syncthreads();
         const int e = tid & 127, half = tid >> 7;
-        const int d = Is[128 + e];
-        const float* x1 = C.tabB + (size_t)d * HS;
+        const float* x1 = X1 + e * PRO_X1_STRIDE;
         float* zt = C.Zt + (size_t)tile * P.z_numel * TILE_E;
         for (int p = 0; p < P.n_paths; ++p) {
           const B200Path pa = P.paths[p];
-          const int d1 = 2 * pa.l1 + 1, k3 = 2 * pa.lo + 1;
-          for (int u = half; u < pa.U; u += 2) {
-            float xv[3];
-            for (int i = 0; i < 3; ++i) xv[i] = (i < d1) ? x1[pa.in1_off + u * d1 + i] : 0.0f;
-            float z0 = 0.f, z1 = 0.f, z2 = 0.f;
-            for (int c = pa.cg_off; c < pa.cg_off + pa.cg_n; ++c) {
-              int ijk = P.cg_ijk[c];
-              int i = ijk & 255, j = (ijk >> 8) & 255, k = (ijk >> 16) & 255;
-              float xi = (i == 0) ? xv[0] : (i == 1 ? xv[1] : xv[2]);
-              float v = P.cg_val[c] * xi * Ss[(pa.in2_off + j) * 128 + e];
-              z0 += (k == 0) ? v : 0.f; z1 += (k == 1) ? v : 0.f; z2 += (k == 2) ? v : 0.f;
-            }
-            float* o = zt + (size_t)(pa.z_off + u * k3) * TILE_E + e;
-            o[0] = z0;
-            if (k3 == 3) { o[TILE_E] = z1; o[2 * TILE_E] = z2; }
-          }
+          const int d1 = 2 * pa.l1 + 1, k3 = 2 * pa.lo + 1, d2 = 2 * pa.l2 + 1;
+          float shv[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) shv[j] = (j < d2) ? Ss[(pa.in2_off + j) * 128 + e] : 0.0f;
+          const float* cg = c_cg_dense[C.plan][p];
+          const float* xp = x1 + pa.in1_off;
+          float* o = zt + (size_t)pa.z_off * TILE_E + e;
+          if (d1 == 1 && k3 == 1) z_path<1, 1>(cg, shv, d2, xp, pa.U, half, 2, o);
+          else if (d1 == 1) z_path<1, 3>(cg, shv, d2, xp, pa.U, half, 2, o);
+          else if (k3 == 1) z_path<3, 1>(cg, shv, d2, xp, pa.U, half, 2, o);
+          else z_path<3, 3>(cg, shv, d2, xp, pa.U, half, 2, o);
         }
       }
     }
@@ -280,43 +332,80 @@ __device__ __forceinline__ void segment_mean_ln(const DevPlan& P, const int* seg
                                                 int n, float* row, int lane) {
   const int p0 = seg[n], p1 = seg[n + 1];
   const float cnt = (float)max(p1 - p0, 1);
-  for (int c = lane; c < P.out_dim; c += 32) {
-    float s = 0.0f;
-    for (int e = p0; e < p1; ++e) s += msg[(size_t)e * HS + c];
-    row[c] = s / cnt;
+  const int nc = (P.out_dim + 31) / 32;
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int e = p0;
+  for (; e + 4 <= p1; e += 4) {                       // 4 rows in flight per lane
+    float v[4][6];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        int c = lane + 32 * q;
+        v[r][q] = (q < nc && c < P.out_dim) ? msg[(size_t)(e + r) * HS + c] : 0.0f;
+      }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s[q] += v[r][q];
+  }
+  for (; e < p1; ++e)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      int c = lane + 32 * q;
+      if (q < nc && c < P.out_dim) s[q] += msg[(size_t)e * HS + c];
+    }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    int c = lane + 32 * q;
+    if (c < P.out_dim) row[c] = s[q] / cnt;
   }
   __syncwarp();
-  float res[6];
-  int ri = 0;
-  for (int c = lane; c < P.out_dim; c += 32, ++ri) {
-    int b = 0;
-    while (b + 1 < P.n_blocks && c >= P.blocks[b + 1].off) ++b;
+  // per-block statistics, lanes split the multiplicity
+  float fm[B200_MAX_BLOCKS][3], scl[B200_MAX_BLOCKS];
+  for (int b = 0; b < P.n_blocks; ++b) {
     const B200Block bl = P.blocks[b];
-    const int u = (c - bl.off) / bl.dim, i = (c - bl.off) % bl.dim;
-    // field mean over the multiplicity for every component, then the mean-shifted squared norm
-    float fm[3] = {0.f, 0.f, 0.f};
-    for (int uu = 0; uu < bl.mul; ++uu)
-      for (int ii = 0; ii < bl.dim; ++ii) fm[ii] += row[bl.off + uu * bl.dim + ii];
-    for (int ii = 0; ii < bl.dim; ++ii) fm[ii] /= (float)bl.mul;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int u = lane; u < bl.mul; u += 32) {
+      const float* r = row + bl.off + u * bl.dim;
+      a0 += r[0];
+      if (bl.dim == 3) { a1 += r[1]; a2 += r[2]; }
+    }
+    a0 = warp_sum(a0) / (float)bl.mul; a1 = warp_sum(a1) / (float)bl.mul; a2 = warp_sum(a2) / (float)bl.mul;
+    fm[b][0] = a0; fm[b][1] = a1; fm[b][2] = a2;
     float nrm = 0.0f;
-    for (int uu = 0; uu < bl.mul; ++uu) {
-      float sq = 0.0f;
-      const float sh = ln.shift[bl.irr_off + uu];
-      for (int ii = 0; ii < bl.dim; ++ii) {
-        float v = row[bl.off + uu * bl.dim + ii] - fm[ii] * sh;
-        sq += v * v;
-      }
+    for (int u = lane; u < bl.mul; u += 32) {
+      const float* r = row + bl.off + u * bl.dim;
+      const float sh = ln.shift[bl.irr_off + u];
+      float v0 = r[0] - a0 * sh, sq = v0 * v0;
+      if (bl.dim == 3) { float v1 = r[1] - a1 * sh, v2 = r[2] - a2 * sh; sq += v1 * v1 + v2 * v2; }
       nrm += sq / (float)bl.dim;
     }
-    nrm /= (float)bl.mul;
-    const float scale = (1.0f / sqrtf(nrm + 1e-5f)) * ln.weight[bl.irr_off + u];
-    float v = (row[c] - fm[i] * ln.shift[bl.irr_off + u]) * scale;
-    if (bl.bias_off >= 0) v += ln.bias[bl.bias_off + u];
-    res[ri] = v;
+    nrm = warp_sum(nrm) / (float)bl.mul;
+    scl[b] = 1.0f / sqrtf(nrm + 1e-5f);
+  }
+  float res[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    int c = lane + 32 * q;
+    res[q] = 0.0f;
+    if (c < P.out_dim) {
+      int b = 0;
+      while (b + 1 < P.n_blocks && c >= P.blocks[b + 1].off) ++b;
+      const B200Block bl = P.blocks[b];
+      const int u = (c - bl.off) / bl.dim, i = (c - bl.off) % bl.dim;
+      const float f = (i == 0) ? fm[b][0] : (i == 1 ? fm[b][1] : fm[b][2]);
+      float v = (row[c] - f * ln.shift[bl.irr_off + u]) * (scl[b] * ln.weight[bl.irr_off + u]);
+      if (bl.bias_off >= 0) v += ln.bias[bl.bias_off + u];
+      res[q] = v;
+    }
   }
   __syncwarp();
-  ri = 0;
-  for (int c = lane; c < P.out_dim; c += 32, ++ri) row[c] = res[ri];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    int c = lane + 32 * q;
+    if (c < P.out_dim) row[c] = res[q];
+  }
   __syncwarp();
 }
 

@@ -302,6 +302,241 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc(ConvLaunch L, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// MODE 3: 3xTF32 with the H1 tile resident in TENSOR MEMORY (A operand from TMEM, "TS" MMA).
+//   TMEM columns: [0,160) tf32(H1)  [160,320) H1 - tf32(H1)  [320,416) D0  [416,512) D1
+//   Shared memory holds only the W2 ring: 8 stages x (96 rows hi + 96 rows lo) x 128 B = 192 KB, i.e.
+//   enough bytes in flight to hide the TMA latency (the smem-resident variant above can keep only two).
+//   The four epilogue warps load their edge's H1 row from global (fp32), split it into TF32 hi/lo in
+//   registers and tcgen05.st it into TMEM at the start of every tile; no H1_lo copy is needed.
+//   Chunks are at most 96 columns wide (plan built with 96-column chunks).
+#define TC3_NST 8
+#define TC3_BN 96
+#define TC3_D0 320
+constexpr size_t TC3_SMEM = 1024 + (size_t)TC3_NST * 2 * TC3_BN * 128 + 256;
+
+namespace tc {
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+}  // namespace tc
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc3(ConvLaunch L, const __grid_constant__ TcMaps maps) {
+  constexpr int BN = TC3_BN, NST = TC3_NST;
+  constexpr uint32_t B_PART = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = base;                                              // [NST][2][96 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)NST * 2 * B_PART);
+  uint64_t* a_full = bars;            uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;        uint64_t* b_empty = bars + 2 + NST;
+  uint64_t* d_full = bars + 2 + 2 * NST;  uint64_t* d_empty = d_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(a_full, 128); tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < NST; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int ci = 0; ci < L.n; ++ci) { tc::prefetch_tmap(&maps.b[ci]); tc::prefetch_tmap(&maps.b_lo[ci]); }
+      tc::Phase st;
+      int tiles_before = 0;
+      for (int ci = 0; ci < L.n; ++ci) {
+        const ConvArgs& C = L.c[ci];
+        const DevPlan& P = c_plans[C.plan];
+        const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
+        int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
+        tiles_before += ntile;
+        for (int tile = first; tile < ntile; tile += gridDim.x) {
+          for (int ch = 0; ch < P.n_chunks; ++ch) {
+            const int col0 = P.chunk_col[ch];
+            for (int ka = 0; ka < TC_KATOMS; ++ka) {
+              tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
+              tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
+              uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
+              tc::tma_load_2d(dst, &maps.b[ci], ka * 32, col0, &b_full[st.idx]);
+              tc::tma_load_2d(dst + B_PART, &maps.b_lo[ci], ka * 32, col0, &b_full[st.idx]);
+              tc::advance(st, NST);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      tc::Phase st, db;
+      uint32_t apar = 0;
+      int tiles_before = 0;
+      for (int ci = 0; ci < L.n; ++ci) {
+        const ConvArgs& C = L.c[ci];
+        const DevPlan& P = c_plans[C.plan];
+        const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
+        int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
+        tiles_before += ntile;
+        for (int tile = first; tile < ntile; tile += gridDim.x) {
+          tc::mbar_wait(a_full, apar);
+          apar ^= 1;
+          tc::fence_after();
+          for (int ch = 0; ch < P.n_chunks; ++ch) {
+            const int N = P.chunk_n[ch];
+            tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
+            tc::fence_after();
+            const uint32_t idesc = tc::make_idesc_tf32(128, N);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(TC3_D0 + db.idx * BN);
+            for (int ka = 0; ka < TC_KATOMS; ++ka) {
+              tc::mbar_wait(&b_full[st.idx], st.par);
+              tc::fence_after();
+              const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * 2 * B_PART);
+              const uint32_t b_lo = b_hi + B_PART;
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) {
+                const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + KP;
+                tc::mma_tf32_ts(d_tmem, a_lo, tc::make_desc(b_hi + k8 * 32), idesc, (ka | k8) ? 1u : 0u);
+                tc::mma_tf32_ts(d_tmem, a_hi, tc::make_desc(b_lo + k8 * 32), idesc, 1u);
+                tc::mma_tf32_ts(d_tmem, a_hi, tc::make_desc(b_hi + k8 * 32), idesc, 1u);
+              }
+              tc::mma_commit(&b_empty[st.idx]);
+              tc::advance(st, NST);
+            }
+            tc::mma_commit(&d_full[db.idx]);
+            tc::advance(db, 2);
+          }
+          tc::mma_commit(a_empty);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    tc::Phase db;
+    uint32_t apar = 0;
+    int tiles_before = 0;
+    for (int ci = 0; ci < L.n; ++ci) {
+      const ConvArgs& C = L.c[ci];
+      const DevPlan& P = c_plans[C.plan];
+      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
+      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
+      tiles_before += ntile;
+      for (int tile = first; tile < ntile; tile += gridDim.x) {
+        // ---- stage this edge's H1 row into tensor memory as TF32 hi / lo
+        tc::mbar_wait(a_empty, apar ^ 1);
+        apar ^= 1;
+        tc::fence_after();
+        {
+          const float4* src = reinterpret_cast<const float4*>(C.H1 + (size_t)(tile * TILE_E + row) * KP);
+#pragma unroll 1
+          for (int g = 0; g < 5; ++g) {
+            float v[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 f = __ldg(src + g * 8 + j);
+              v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              uint32_t hb;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
+              float hi = __uint_as_float(hb);
+              lo[j] = v[j] - hi; v[j] = hi;
+            }
+            tc::tmem_st32(lane_base + (uint32_t)(g * 32), v);
+            tc::tmem_st32(lane_base + (uint32_t)(KP + g * 32), lo);
+          }
+          tc::tmem_wait_st();
+          tc::fence_before();
+          tc::mbar_arrive(a_full);
+        }
+        const float* zt = C.Zt + (size_t)tile * P.z_numel * TILE_E + row;
+        float* mrow = C.msg + (size_t)(tile * TILE_E + row) * HS;
+        float o[48];
+#pragma unroll
+        for (int i = 0; i < 48; ++i) o[i] = 0.0f;
+        for (int ch = 0; ch < P.n_chunks; ++ch) {
+          const int col0 = P.chunk_col[ch], N = P.chunk_n[ch];
+          const B200Path pa = P.paths[P.chunk_path[ch]];
+          const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
+          tc::mbar_wait(&d_full[db.idx], db.par);
+          tc::fence_after();
+          const uint32_t taddr = lane_base + (uint32_t)(TC3_D0 + db.idx * BN);
+          if (pa.Wd == 48) {
+            for (int uu = 0; uu < nu; ++uu) {
+              float v[48];
+              tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
+              const float z = zt[(size_t)(pa.z_off + u0 + uu) * TILE_E];
+              tc::tmem_wait_ld();
+#pragma unroll
+              for (int w = 0; w < 48; ++w) o[w] = fmaf(v[w], z, o[w]);
+            }
+          } else {
+            for (int uu = 0; uu < nu; ++uu) {
+              float v[12];
+              tc::tmem_ld4(taddr + uu * 12, v); tc::tmem_ld4(taddr + uu * 12 + 4, v + 4); tc::tmem_ld4(taddr + uu * 12 + 8, v + 8);
+              const float* zp = zt + (size_t)(pa.z_off + (u0 + uu) * 3) * TILE_E;
+              const float z0 = zp[0], z1 = zp[TILE_E], z2 = zp[2 * TILE_E];
+              tc::tmem_wait_ld();
+#pragma unroll
+              for (int w = 0; w < 12; ++w) {
+                o[w * 3] = fmaf(v[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(v[w], z1, o[w * 3 + 1]);
+                o[w * 3 + 2] = fmaf(v[w], z2, o[w * 3 + 2]);
+              }
+            }
+          }
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&d_empty[db.idx]);
+          tc::advance(db, 2);
+          bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
+          if (last) {
+            const int nout = (pa.Wd == 48) ? 48 : 36;
+#pragma unroll
+            for (int i = 0; i < 48; i += 4) {
+              if (i < nout) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+              o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -317,6 +552,7 @@ static inline int conv_tc_init() {
   }
   if (cudaFuncSetAttribute(k_conv_tp_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()) != cudaSuccess) return 2;
   if (cudaFuncSetAttribute(k_conv_tp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<1>()) != cudaSuccess) return 3;
+  if (cudaFuncSetAttribute(k_conv_tp_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC3_SMEM) != cudaSuccess) return 4;
   return 0;
 }
 
@@ -339,16 +575,15 @@ static inline int launch_conv_tc(const ConvLaunch& L, const TcExtra& X, int mode
   if (!g_encode) return 1;
   TcMaps maps;
   memset(&maps, 0, sizeof maps);
-  const uint32_t bn = (mode == 2) ? TcCfg<2>::BN : TcCfg<1>::BN;
+  const uint32_t bn = (mode == 2) ? TcCfg<2>::BN : (mode == 3 ? TC3_BN : TcCfg<1>::BN);
   for (int i = 0; i < L.n; ++i) {
-    if (tc_make_map(&maps.a[i], L.c[i].H1, X.h1_rows[i], 128)) return 2;
+    if (mode != 3 && tc_make_map(&maps.a[i], L.c[i].H1, X.h1_rows[i], 128)) return 2;
     if (tc_make_map(&maps.b[i], L.c[i].W2p, X.w2_rows[i], bn)) return 3;
-    if (mode == 1) {
-      if (tc_make_map(&maps.a_lo[i], X.H1_lo[i], X.h1_rows[i], 128)) return 4;
-      if (tc_make_map(&maps.b_lo[i], X.W2_lo[i], X.w2_rows[i], bn)) return 5;
-    }
+    if (mode == 1 && tc_make_map(&maps.a_lo[i], X.H1_lo[i], X.h1_rows[i], 128)) return 4;
+    if (mode != 2 && tc_make_map(&maps.b_lo[i], X.W2_lo[i], X.w2_rows[i], bn)) return 5;
   }
   if (mode == 2) k_conv_tp_tc<2><<<n_sms, TC_THREADS, tc_smem_bytes<2>(), st>>>(L, maps);
+  else if (mode == 3) k_conv_tp_tc3<<<n_sms, TC_THREADS, TC3_SMEM, st>>>(L, maps);
   else k_conv_tp_tc<1><<<n_sms, TC_THREADS, tc_smem_bytes<1>(), st>>>(L, maps);
   return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }

@@ -97,7 +97,8 @@ def sinusoidal_embedding(t: torch.Tensor, dim: int = 32, scale: float = 1000.0) 
 
 
 class Engine:
-    """One handle = one device.  ``conv_kernel``: 0 SIMT fp32, 1 tcgen05 TF32x3, 2 tcgen05 TF32."""
+    """One handle = one device.  ``conv_kernel``: 0 SIMT fp32 (exact), 1 tcgen05 3xTF32 (H1 in smem),
+    2 tcgen05 single TF32 (fast, ~1e-3), 3 tcgen05 3xTF32 with H1 resident in tensor memory (default)."""
 
     def __init__(self, device: int = 0, conv_kernel: int = 0):
         if not torch.cuda.is_available():

@@ -68,13 +68,13 @@ def plan_specs() -> List[spec.TPSpec]:
     return [spec.conv_tp(0), spec.conv_tp(1), spec.conv_tp(2), spec.conv_tp(3), spec.tor_tp(), spec.final_tp()]
 
 
-def chunks_of(tp: spec.TPSpec) -> List[Tuple[int, int, int]]:
+def chunks_of(tp: spec.TPSpec, cols: int = CHUNK_COLS) -> List[Tuple[int, int, int]]:
     """(first column, n columns, path index): whole-u slices of one path, at most 192 columns, ordered so
     that all chunks feeding one output irreps block are consecutive (the tensor-core epilogue keeps that
     block in registers and stores it once)."""
     out = []
     for pi, p in sorted(enumerate(tp.paths), key=lambda t: (t[1].out_off, t[0])):   # grouped by output block
-        upc = max(CHUNK_COLS // p.mulo, 1)
+        upc = max(cols // p.mulo, 1)
         for u0 in range(0, p.mul1, upc):
             nu = min(upc, p.mul1 - u0)
             out.append((p.w_off + u0 * p.mulo, nu * p.mulo, pi))
@@ -122,7 +122,7 @@ class Plans:
                 off += m * (2 * l + 1)
                 irr += m
             ijk = np.ascontiguousarray(np.concatenate(ijk_all)); val = np.ascontiguousarray(np.concatenate(val_all))
-            ch = np.asarray(chunks_of(tp), dtype=np.int32)
+            ch = np.asarray(chunks_of(tp, 96 if conv_kernel == 3 else CHUNK_COLS), dtype=np.int32)
             cc, cn, cpth = (np.ascontiguousarray(ch[:, k]) for k in range(3))
             self.keep += [ijk, val, cc, cn, cpth]
             cp.n_cg = len(ijk)

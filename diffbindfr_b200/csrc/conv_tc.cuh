@@ -104,6 +104,11 @@ __device__ __forceinline__ void tmem_ld4(uint32_t addr, float* v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 struct Phase { uint32_t idx = 0, par = 0; };
 __device__ __forceinline__ void advance(Phase& p, int n) { if (++p.idx == (uint32_t)n) { p.idx = 0; p.par ^= 1; } }
 
@@ -143,8 +148,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc(ConvLaunch L, cons
 
   // Every role walks the same (conv, tile, chunk, sub-chunk, k-atom) sequence.
   if (warp == 0) {
-    if (lane == 0) {
-      for (int ci = 0; ci < L.n; ++ci) { tc::prefetch_tmap(&maps.a[ci]); tc::prefetch_tmap(&maps.b[ci]); }
+    {
+      if (lane == 0) for (int ci = 0; ci < L.n; ++ci) { tc::prefetch_tmap(&maps.a[ci]); tc::prefetch_tmap(&maps.b[ci]); }
+      __syncwarp();
       tc::Phase st, at;   // B ring stage / A tile phase
       int tiles_before = 0;
       for (int ci = 0; ci < L.n; ++ci) {
@@ -155,21 +161,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc(ConvLaunch L, cons
         tiles_before += ntile;
         for (int tile = first; tile < ntile; tile += gridDim.x) {
           tc::mbar_wait(a_empty, at.par ^ 1);
-          tc::mbar_expect_tx(a_full, NSPLIT * A_BYTES);
-          for (int ka = 0; ka < TC_KATOMS; ++ka) {
-            tc::tma_load_2d(sA + ka * TC_A_ATOM_BYTES, &maps.a[ci], ka * 32, tile * TILE_E, a_full);
-            if (NSPLIT == 2) tc::tma_load_2d(sA + A_BYTES + ka * TC_A_ATOM_BYTES, &maps.a_lo[ci], ka * 32, tile * TILE_E, a_full);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(a_full, NSPLIT * A_BYTES);
+            for (int ka = 0; ka < TC_KATOMS; ++ka) {
+              tc::tma_load_2d(sA + ka * TC_A_ATOM_BYTES, &maps.a[ci], ka * 32, tile * TILE_E, a_full);
+              if (NSPLIT == 2) tc::tma_load_2d(sA + A_BYTES + ka * TC_A_ATOM_BYTES, &maps.a_lo[ci], ka * 32, tile * TILE_E, a_full);
+            }
           }
+          __syncwarp();
           at.par ^= 1;
           for (int ch = 0; ch < P.n_chunks; ++ch) {
             const int col0 = P.chunk_col[ch], N = P.chunk_n[ch];
             for (int sub = 0; sub * BN < N; ++sub) {
               for (int ka = 0; ka < TC_KATOMS; ++ka) {
                 tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
-                tc::mbar_expect_tx(&b_full[st.idx], NSPLIT * B_PART);
-                uint8_t* dst = sB + (size_t)st.idx * NSPLIT * B_PART;
-                tc::tma_load_2d(dst, &maps.b[ci], ka * 32, col0 + sub * BN, &b_full[st.idx]);
-                if (NSPLIT == 2) tc::tma_load_2d(dst + B_PART, &maps.b_lo[ci], ka * 32, col0 + sub * BN, &b_full[st.idx]);
+                if (tc::elect_one()) {
+                  tc::mbar_expect_tx(&b_full[st.idx], NSPLIT * B_PART);
+                  uint8_t* dst = sB + (size_t)st.idx * NSPLIT * B_PART;
+                  tc::tma_load_2d(dst, &maps.b[ci], ka * 32, col0 + sub * BN, &b_full[st.idx]);
+                  if (NSPLIT == 2) tc::tma_load_2d(dst + B_PART, &maps.b_lo[ci], ka * 32, col0 + sub * BN, &b_full[st.idx]);
+                }
+                __syncwarp();
                 tc::advance(st, NST);
               }
             }
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc(ConvLaunch L, cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       tc::Phase st, at, db;  // B ring, A tile, D buffer
       int tiles_before = 0;
       for (int ci = 0; ci < L.n; ++ci) {
@@ -196,7 +208,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc(ConvLaunch L, cons
             const int N = P.chunk_n[ch];
             tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
             tc::fence_after();
-            for (int sub = 0; sub * BN < N; ++sub) {
+            const int nsubs = (N + BN - 1) / BN;
+            for (int sub = 0; sub < nsubs; ++sub) {
               const int nsub = min(BN, N - sub * BN);
               const uint32_t idesc = tc::make_idesc_tf32(128, nsub);
               const uint32_t d_tmem = tmem_base + (uint32_t)(db.idx * TC_DCOLS + sub * BN);
@@ -205,26 +218,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc(ConvLaunch L, cons
                 tc::fence_after();
                 const uint32_t a_hi = tc::smem_u32(sA + ka * TC_A_ATOM_BYTES);
                 const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * NSPLIT * B_PART);
+                const uint64_t ah = tc::make_desc(a_hi), bh = tc::make_desc(b_hi);
+                const uint64_t al = tc::make_desc(a_hi + A_BYTES), bl = tc::make_desc(b_hi + B_PART);
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int k8 = 0; k8 < 4; ++k8) {
-                  const uint32_t acc0 = (ka | k8) ? 1u : 0u;
-                  if (NSPLIT == 1) {
-                    tc::mma_tf32(d_tmem, tc::make_desc(a_hi + k8 * 32), tc::make_desc(b_hi + k8 * 32), idesc, acc0);
-                  } else {
-                    const uint32_t a_lo = a_hi + A_BYTES, b_lo = b_hi + B_PART;
-                    tc::mma_tf32(d_tmem, tc::make_desc(a_lo + k8 * 32), tc::make_desc(b_hi + k8 * 32), idesc, acc0);
-                    tc::mma_tf32(d_tmem, tc::make_desc(a_hi + k8 * 32), tc::make_desc(b_lo + k8 * 32), idesc, 1u);
-                    tc::mma_tf32(d_tmem, tc::make_desc(a_hi + k8 * 32), tc::make_desc(b_hi + k8 * 32), idesc, 1u);
+                  for (int k8 = 0; k8 < 4; ++k8) {
+                    const uint32_t acc0 = (ka | k8) ? 1u : 0u;
+                    const uint64_t o = (uint64_t)(k8 * 2);
+                    if (NSPLIT == 1) {
+                      tc::mma_tf32(d_tmem, ah + o, bh + o, idesc, acc0);
+                    } else {
+                      tc::mma_tf32(d_tmem, al + o, bh + o, idesc, acc0);
+                      tc::mma_tf32(d_tmem, ah + o, bl + o, idesc, 1u);
+                      tc::mma_tf32(d_tmem, ah + o, bh + o, idesc, 1u);
+                    }
+                  }
+                  tc::mma_commit(&b_empty[st.idx]);   // frees the W2 stage when these MMAs retire
+                  if (ka == TC_KATOMS - 1 && sub + 1 == nsubs) {
+                    tc::mma_commit(&d_full[db.idx]);  // accumulator buffer ready for the epilogue
+                    if (ch + 1 == P.n_chunks) tc::mma_commit(a_empty);   // H1 tile may be overwritten
                   }
                 }
-                tc::mma_commit(&b_empty[st.idx]);   // frees the W2 stage when these MMAs retire
+                __syncwarp();
                 tc::advance(st, NST);
               }
             }
-            tc::mma_commit(&d_full[db.idx]);        // accumulator buffer ready for the epilogue
             tc::advance(db, 2);
           }
-          tc::mma_commit(a_empty);                  // H1 tile may be overwritten
         }
       }
     }
@@ -365,8 +385,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc3(ConvLaunch L, con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int ci = 0; ci < L.n; ++ci) { tc::prefetch_tmap(&maps.b[ci]); tc::prefetch_tmap(&maps.b_lo[ci]); }
+    {
+      if (lane == 0) for (int ci = 0; ci < L.n; ++ci) { tc::prefetch_tmap(&maps.b[ci]); tc::prefetch_tmap(&maps.b_lo[ci]); }
+      __syncwarp();
       tc::Phase st;
       int tiles_before = 0;
       for (int ci = 0; ci < L.n; ++ci) {
@@ -380,10 +401,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc3(ConvLaunch L, con
             const int col0 = P.chunk_col[ch];
             for (int ka = 0; ka < TC_KATOMS; ++ka) {
               tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
-              tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
-              uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
-              tc::tma_load_2d(dst, &maps.b[ci], ka * 32, col0, &b_full[st.idx]);
-              tc::tma_load_2d(dst + B_PART, &maps.b_lo[ci], ka * 32, col0, &b_full[st.idx]);
+              if (tc::elect_one()) {
+                tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
+                uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
+                tc::tma_load_2d(dst, &maps.b[ci], ka * 32, col0, &b_full[st.idx]);
+                tc::tma_load_2d(dst + B_PART, &maps.b_lo[ci], ka * 32, col0, &b_full[st.idx]);
+              }
+              __syncwarp();
               tc::advance(st, NST);
             }
           }
@@ -392,7 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc3(ConvLaunch L, con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       tc::Phase st, db;
       uint32_t apar = 0;
       int tiles_before = 0;
@@ -416,21 +440,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tp_tc3(ConvLaunch L, con
               tc::mbar_wait(&b_full[st.idx], st.par);
               tc::fence_after();
               const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * 2 * B_PART);
-              const uint32_t b_lo = b_hi + B_PART;
+              const uint64_t dh = tc::make_desc(b_hi), dl = tc::make_desc(b_hi + B_PART);
+              if (tc::elect_one()) {
 #pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) {
-                const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + KP;
-                tc::mma_tf32_ts(d_tmem, a_lo, tc::make_desc(b_hi + k8 * 32), idesc, (ka | k8) ? 1u : 0u);
-                tc::mma_tf32_ts(d_tmem, a_hi, tc::make_desc(b_lo + k8 * 32), idesc, 1u);
-                tc::mma_tf32_ts(d_tmem, a_hi, tc::make_desc(b_hi + k8 * 32), idesc, 1u);
+                for (int k8 = 0; k8 < 4; ++k8) {
+                  const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + KP;
+                  tc::mma_tf32_ts(d_tmem, a_lo, dh + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
+                  tc::mma_tf32_ts(d_tmem, a_hi, dl + (uint64_t)(k8 * 2), idesc, 1u);
+                  tc::mma_tf32_ts(d_tmem, a_hi, dh + (uint64_t)(k8 * 2), idesc, 1u);
+                }
+                tc::mma_commit(&b_empty[st.idx]);
+                if (ka == TC_KATOMS - 1) {
+                  tc::mma_commit(&d_full[db.idx]);
+                  if (ch + 1 == P.n_chunks) tc::mma_commit(a_empty);
+                }
               }
-              tc::mma_commit(&b_empty[st.idx]);
+              __syncwarp();
               tc::advance(st, NST);
             }
-            tc::mma_commit(&d_full[db.idx]);
             tc::advance(db, 2);
           }
-          tc::mma_commit(a_empty);
         }
       }
     }

@@ -1,0 +1,14 @@
+# DiffBindFR config that routes the hot path through the B200 plugin; everything else is inherited.
+# Usage (reference CLI unchanged):  python DiffBindFR/app/predict.py ... -cfg <this file>
+# The reference's mmcv-style Config honours `_base_` and `custom_imports` (druglib/utils/config.py:321-328).
+_base_ = ['../DiffBindFR/configs/diffbindfr_ts.py']   # adjust to where the reference checkout lives
+
+custom_imports = dict(imports=['diffbindfr_b200.plugin'], allow_failed_imports=False)
+
+model = dict(
+    type='DiffBindFRB200',
+    diffusion_model=dict(
+        type='TensorProductModelB200',
+        conv_kernel=3,   # 3: tcgen05 3xTF32 (fp32-grade, default); 2: tcgen05 TF32 (fast, ~1e-3); 0: fp32 SIMT
+    ),
+)

@@ -1,0 +1,261 @@
+"""Drop-in mirror of the reference's model classes for the hot path, backed by libb200dock.
+
+Reference interfaces mirrored (same constructor arguments, call signatures, return values,
+side effects on ``data`` and ``state_dict`` keys):
+
+* ``TensorProductModel(cfg)`` / ``forward(data) -> (tr, rot, tor, sc_tor)``
+  druglib/models/Docking/interaction/tpscore.py:202-573 (registered in ``INTERACTION``)
+* ``DiffBindFR(diffusion_model, scoring_model, train_cfg, test_cfg, pretrained, init_cfg)`` /
+  ``forward(data, mode='test', visualize=False)`` / ``sample(data, visualize)``
+  druglib/models/Docking/scFlex.py:26-250 (registered in ``MLDOCK_BUILDER``)
+
+Selection without touching ``DiffBindFR/app/predict.py``: a config that lists this module in
+``custom_imports`` and sets ``model.type='DiffBindFRB200'``,
+``model.diffusion_model.type='TensorProductModelB200'`` (configs/diffbindfr_ts_b200.py), see
+INTEGRATION.md.  ``register()`` is called on import and is a no-op when ``druglib`` is absent.
+
+There is no CPU fallback: ``forward`` raises if CUDA or the extension is unavailable.
+"""
+from __future__ import annotations
+
+import copy
+import re
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import schedule as sched
+from . import spec
+from .engine import Engine
+
+_TP_BUFFER = re.compile(r"(\.tp\.|^final_tp_tor\.|\.final_tp_tor\.)")
+
+
+def _get(obj, key, default=None):
+    if isinstance(obj, dict):
+        return obj.get(key, default)
+    return getattr(obj, key, default)
+
+
+def _set(obj, key, value):
+    if isinstance(obj, dict):
+        obj[key] = value
+    else:
+        setattr(obj, key, value)
+
+
+def _pop(obj, key):
+    if hasattr(obj, "pop"):
+        return obj.pop(key)
+    v = getattr(obj, key)
+    delattr(obj, key)
+    return v
+
+
+class _Node(nn.Module):
+    """Container used to reproduce the reference's dotted parameter names exactly."""
+
+
+def _attach(root: nn.Module, dotted: str, tensor: torch.Tensor, buffer: bool = False):
+    parts = dotted.split(".")
+    m = root
+    for p in parts[:-1]:
+        if not hasattr(m, p):
+            m.add_module(p, _Node())
+        m = getattr(m, p)
+    if buffer:
+        m.register_buffer(parts[-1], tensor)
+    else:
+        m.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+_EXPECTED_CFG = dict(ns=spec.NS, nv=spec.NV, sh_lmax=2, lig_cutoff=5, atom_cutoff=4, cross_cutoff=32,
+                     dynamic_max_cross=True, center_max_distance=32, atom_max_neighbors=1000, distance_embed_dim=32,
+                     sigma_embed_dim=32, emb_scale=1000, num_conv_layers=6, use_second_order_repr=False,
+                     batch_norm=True, scale_by_sigma=True, no_sc_torsion=False, task="struct_gen",
+                     time_emb_type="sinusoidal")
+
+
+class TensorProductModel(nn.Module):
+    """B200 implementation of the SE(3)-equivariant score network (same state_dict as the reference)."""
+
+    def __init__(self, cfg=None, conv_kernel: int = 3, device: Optional[int] = None):
+        super().__init__()
+        self.cfg = cfg
+        if cfg is not None:
+            for k, v in _EXPECTED_CFG.items():
+                got = _get(cfg, k, v)
+                if got != v:
+                    raise NotImplementedError(
+                        f"TensorProductModelB200 implements the shipped DiffBindFR architecture only: cfg.{k}={got!r}, "
+                        f"expected {v!r} (DiffBindFR/configs/diffbindfr_ts.py:107-142)")
+        self.no_sc_torsion = False
+        self.conv_kernel = conv_kernel
+        self._device_index = device
+        g = torch.Generator().manual_seed(0)
+        for name, shape in spec.param_shapes():
+            fan = shape[-1] if len(shape) > 1 else 1
+            _attach(self, name, (torch.rand(shape, generator=g) * 2 - 1) / max(fan, 1) ** 0.5)
+        for name, shape in spec.buffer_shapes():
+            base = name.rsplit(".", 1)[0]
+            off = torch.linspace(0.0, spec.GAUSSIAN_STOPS[base], spec.DIST_EMB)
+            _attach(self, name, off if name.endswith("offset") else (-0.5 / (off[1] - off[0]) ** 2), buffer=True)
+        self._engine: Optional[Engine] = None
+        self._packed = False
+
+    # e3nn registers non-parameter buffers under *.tp.* whose keys cannot be enumerated without e3nn;
+    # accept and ignore them so that reference checkpoints load with strict=True.
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        sd = {k: v for k, v in state_dict.items() if not _TP_BUFFER.search(k)}
+        out = super().load_state_dict(sd, strict=strict, **kw)
+        self._packed = False
+        return out
+
+    def init_weights(self):
+        return None
+
+    def engine(self) -> Engine:
+        if not torch.cuda.is_available():
+            raise RuntimeError("TensorProductModelB200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if self._engine is None:
+            dev = self._device_index if self._device_index is not None else torch.cuda.current_device()
+            self._engine = Engine(dev, conv_kernel=self.conv_kernel)
+        if not self._packed:
+            self._engine.load_state_dict({k: v.detach().cpu() for k, v in self.state_dict().items()})
+            self._packed = True
+        return self._engine
+
+    def forward(self, data):
+        eng = self.engine()
+        lb = _get(data, "lig_node_batch")
+        B = int(lb.max().item()) + 1
+        _set(data, "num_graphs", B)
+        t = _get(data, "t")
+        from .engine import sinusoidal_embedding
+        _set(data, "time_emb", sinusoidal_embedding(t.detach().cpu()).to(t.device))
+        tr_sigma = _get(data, "tr_sigma")
+        batch = _as_batch_dict(data)
+        n_tor = int(batch["tor_edge_mask"].sum())
+        tor_n2 = _get(data, "tor_score_norm2") if n_tor else torch.zeros(0)
+        tr, rot, tor, sc = eng.score(batch, t.detach().cpu(), tr_sigma.detach().cpu(), _get(data, "rot_score_norm").detach().cpu(),
+                                     tor_n2.detach().cpu(), _get(data, "sc_tor_score_norm2").detach().cpu())
+        # side effects of the reference forward (tpscore.py:463-483,567)
+        _set(data, "tr_sigma", tr_sigma.unsqueeze(1))
+        scm = torch.as_tensor(batch["sc_torsion_edge_mask"]).bool()
+        tei = _pop(data, "torsion_edge_index")
+        _set(data, "sc_torsion_edge_index", tei[scm.to(tei.device)].T)
+        _set(data, "sc_tor_score_norm2", _get(data, "sc_tor_score_norm2")[scm.to(tei.device)])
+        return tr, rot, tor, sc
+
+
+def _as_batch_dict(data) -> Dict[str, object]:
+    keys = ["lig_node", "lig_pos", "lig_edge_index", "lig_edge_feat", "tor_edge_mask", "pocket_node_feature", "rec_atm_pos",
+            "atom14_mask", "sequence", "backbone_transl", "backbone_rots", "default_frame", "rigid_group_positions",
+            "torsion_angle", "torsion_edge_index", "sc_torsion_edge_mask", "lig_node_batch", "rec_atm_pos_batch"]
+    out = {k: _get(data, k) for k in keys}
+    meta = _get(data, "metastore")
+    rm = meta["rot_node_mask"] if meta is not None else _get(data, "rot_node_mask")
+    out["rot_node_mask"] = [m.detach().cpu().numpy() if torch.is_tensor(m) else np.asarray(m) for m in rm]
+    out["num_graphs"] = int(torch.as_tensor(out["lig_node_batch"]).max()) + 1
+    return out
+
+
+class DiffBindFR(nn.Module):
+    """Reverse-SDE sampler (scFlex.py:26-250) on the device: all ``actual_steps`` steps run inside one
+    C-ABI call; noise is drawn on the host from torch's default generator in the reference's order."""
+
+    def __init__(self, diffusion_model: Optional[dict] = None, scoring_model: Optional[dict] = None,
+                 train_cfg: dict = {}, test_cfg: dict = {}, pretrained=None, init_cfg: dict = {}, **kwargs):
+        super().__init__()
+        if scoring_model is not None:
+            raise NotImplementedError("the MDN scoring model is not part of the B200 plugin yet (SURVEY.md 8(a) row a21)")
+        if diffusion_model is not None:
+            self.diffusion_model_cfg = copy.deepcopy(_get(diffusion_model, "cfg"))
+            dm = diffusion_model
+            if isinstance(dm, nn.Module):
+                self.diffusion_model = dm
+            else:
+                self.diffusion_model = TensorProductModel(_get(dm, "cfg"), conv_kernel=int(_get(dm, "conv_kernel", 3)))
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.pretrain, self.init_cfg = pretrained, init_cfg
+        self._schedule = None
+
+    def init_weights(self):
+        return None
+
+    def forward_train(self, **kwargs):
+        raise RuntimeError("DiffBindFRB200 is an inference plugin; training runs on the reference implementation")
+
+    def forward(self, data, mode: str = "test", visualize: bool = False, **kwargs):
+        if mode != "test":
+            return self.forward_train(**kwargs)
+        if hasattr(data, "to_dict"):
+            data = data.to_dict(decode=True, drop_meta=False)
+        return self.sample(data, visualize=visualize)
+
+    def sample_cfg(self) -> spec.SampleCfg:
+        c = _get(self.test_cfg, "sample_cfg", None) if self.test_cfg else None
+        out = spec.SampleCfg()
+        if c is not None:
+            for f in out.__dataclass_fields__:
+                v = _get(c, f, None)
+                if v is not None:
+                    setattr(out, f, v)
+        if out.time_schedule != "linear":
+            raise NotImplementedError("Current time schedule only supports `linear`.")
+        if out.actual_steps > out.inference_steps:
+            raise AssertionError("actual steps should <= inference steps")
+        return out
+
+    @torch.no_grad()
+    def sample(self, data, visualize: bool = False):
+        cfg = self.sample_cfg()
+        if self._schedule is None or self._schedule[0] != cfg:
+            self._schedule = (copy.copy(cfg), sched.make_schedule(cfg))
+        steps = self._schedule[1]
+        batch = _as_batch_dict(data)
+        B = batch["num_graphs"]
+        n_tor, n_sc = int(batch["tor_edge_mask"].sum()), int(torch.as_tensor(batch["sc_torsion_edge_mask"]).sum())
+        noise = []
+        for i in range(cfg.actual_steps):   # same draw order as scFlex.py:167-183,202-204
+            zero = cfg.no_random or (cfg.no_final_step_noise and i == cfg.actual_steps - 1) or cfg.type == "ode"
+            f = (lambda *s: torch.zeros(*s)) if zero else (lambda *s: torch.normal(mean=0, std=1, size=s))
+            noise.append(dict(tr=f(B, 3), rot=f(B, 3), tor=f(n_tor), sc=f(n_sc)))
+        eng = self.diffusion_model.engine()
+        lig, a14, lig_traj, a14_traj = eng.sample(batch, steps, Engine.pack_noise(noise), trajectory=visualize,
+                                                  ode=(cfg.type == "ode"))
+        if visualize:
+            lig_t, a14_t = lig_traj.cpu(), a14_traj.cpu()                 # (T, N_l, 3), (T, N_r, 14, 3)
+        else:
+            lig_t, a14_t = lig.cpu().unsqueeze(0), a14.cpu().unsqueeze(0)
+        lb = torch.as_tensor(batch["lig_node_batch"]).cpu()
+        amask = torch.as_tensor(batch["atom14_mask"]).bool().cpu()
+        ab = torch.as_tensor(batch["rec_atm_pos_batch"]).cpu()
+        batch14 = torch.zeros(amask.shape, dtype=torch.long)
+        batch14[amask] = ab
+        res_b = torch.amax(batch14, dim=-1)                               # slice_protein (scFlex.py:307-313)
+        out = []
+        for g in range(B):
+            out.append((lig_t[:, lb == g], a14_t[:, res_b == g]))
+        return out
+
+
+def register(force: bool = True) -> bool:
+    """Register the plugin classes in the reference's registries when ``druglib`` is importable."""
+    try:
+        from druglib.models.builder import INTERACTION  # type: ignore
+        from druglib.models.Docking.default_MLDockBuilder import MLDOCK_BUILDER  # type: ignore
+    except Exception:
+        return False
+    try:
+        INTERACTION.register_module(name="TensorProductModelB200", force=force, module=TensorProductModel)
+        MLDOCK_BUILDER.register_module(name="DiffBindFRB200", force=force, module=DiffBindFR)
+    except TypeError:
+        INTERACTION.register_module(name="TensorProductModelB200", module=TensorProductModel)
+        MLDOCK_BUILDER.register_module(name="DiffBindFRB200", module=DiffBindFR)
+    return True
+
+
+register()

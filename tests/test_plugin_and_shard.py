@@ -1,0 +1,104 @@
+"""CPU tests: plugin state_dict contract / registry surface, and the N>1 sharding + gather (gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffbindfr_b200 import plugin, shard, spec, synth, weights
+
+
+def test_plugin_state_dict_matches_reference_contract():
+    m = plugin.TensorProductModel(None)
+    keys = list(m.state_dict().keys())
+    want = [k for k, _ in spec.param_shapes()] + [k for k, _ in spec.buffer_shapes()]
+    assert sorted(keys) == sorted(want)
+    sd = weights.random_state_dict(3)
+    sd["lig_conv_layers.0.tp.output_mask"] = torch.ones(84)          # e3nn buffers are tolerated
+    sd["final_tp_tor.weight"] = torch.empty(0)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m.state_dict()["tor_bond_conv.fc.lin.3.weight"], sd["tor_bond_conv.fc.lin.3.weight"])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({k: v for k, v in sd.items() if "tr_final_layer" not in k}, strict=True)
+
+
+def test_plugin_rejects_unsupported_architecture():
+    with pytest.raises(NotImplementedError):
+        plugin.TensorProductModel(dict(ns=32))
+    with pytest.raises(NotImplementedError):
+        plugin.DiffBindFR(diffusion_model=dict(cfg=None), scoring_model=dict(cfg={}))
+
+
+@pytest.mark.reference
+def test_plugin_state_dict_equals_reference_module():
+    from oracle import shims
+    shims.install()
+    from druglib.models.Docking.interaction.tpscore import TensorProductModel as Ref
+    ref = Ref(shims.reference_model_cfg())
+    ours = plugin.TensorProductModel(shims.reference_model_cfg())
+    res = ours.load_state_dict(ref.state_dict(), strict=True)       # includes the e3nn-like tp buffers
+    assert not res.missing_keys and not res.unexpected_keys
+    assert [k for k, _ in ref.named_parameters()] == [k for k, _ in ours.named_parameters()]
+
+
+@pytest.mark.reference
+def test_plugin_registers_in_reference_registries():
+    from oracle import shims
+    shims.install()
+    assert plugin.register()
+    from druglib.models.builder import INTERACTION
+    from druglib.models.Docking.default_MLDockBuilder import MLDOCK_BUILDER
+    assert INTERACTION.module_dict["TensorProductModelB200"] is plugin.TensorProductModel
+    assert MLDOCK_BUILDER.module_dict["DiffBindFRB200"] is plugin.DiffBindFR
+
+
+def test_forward_without_cuda_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    m = plugin.TensorProductModel(None)
+    with pytest.raises(RuntimeError):
+        m.engine()
+
+
+def test_shard_indices_partition():
+    for n, w in ((40, 8), (41, 4), (3, 8)):
+        parts = [shard.shard_indices(n, r, w) for r in range(w)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    samples = [synth.make_sample(rng, 6 + (i % 3), 8 + (i % 5)) for i in range(7)]   # ragged sizes, odd count
+
+    def run_batch(chunk):   # stand-in for the device sampler: a rank-independent function of the inputs
+        return [(torch.from_numpy(s["lig_pos"]) * 2 + 1, torch.from_numpy(s["atom14_position"]) - 3) for s in chunk]
+
+    got = shard.run_sharded(samples, run_batch, batch_size=2)
+    ok = sorted(got) == list(range(7))
+    for i, s in enumerate(samples):
+        ok &= torch.allclose(got[i][0], torch.from_numpy(s["lig_pos"]) * 2 + 1)
+        ok &= torch.allclose(got[i][1], torch.from_numpy(s["atom14_position"]) - 3)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_and_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    assert sorted(res) == [(0, True), (1, True)]

@@ -150,7 +150,11 @@ def test_ragged_and_empty_cases(engines, sd):
 
 
 class _AttrDict(dict):
-    __getattr__ = dict.__getitem__
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
     __setattr__ = dict.__setitem__
     __delattr__ = dict.__delitem__
 

@@ -12,6 +12,7 @@
 #include "embed.cuh"
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "conv_fused.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
 
@@ -40,6 +41,7 @@ struct ConvWs {                 // per edge family: lig, atom, al, la, tor, sc
 struct ConvW {                  // views into the device weight blob
   const float *W1t, *b1, *W2p; LnParams ln;
   const float *W2hi = nullptr, *W2lo = nullptr; int n_cols = 0;
+  const float *W1hi = nullptr, *W1lo = nullptr;
 };
 
 }  // namespace
@@ -52,7 +54,7 @@ struct B200Handle {
   DevPlan dplans[B200_N_PLANS];
   std::vector<void*> plan_allocs;
   int* d_tor_cg_ijk = nullptr; float* d_tor_cg_val = nullptr;
-  float* d_blob = nullptr; float* d_w2split = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
+  float* d_blob = nullptr; float* d_w2split = nullptr; float* d_w1p = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
   ConvW convw[26];
   // workspace
   ConvWs cw[6];
@@ -128,9 +130,12 @@ int setup_workspace(B200Handle* h, const B200Batch& b) {
     ENS(w.es, (size_t)w.cap * 4); ENS(w.ed, (size_t)w.cap * 4);
     if (c == 0) ENS(w.eaux, (size_t)w.cap * 4);
     ENS(w.emb, (size_t)w.cap * NSC * 4); ENS(w.sh, (size_t)w.cap * 9 * 4);
-    ENS(w.H1, (size_t)w.cap * KP * 4);
-    if (h->cfg.conv_kernel == 1) ENS(w.H1lo, (size_t)w.cap * KP * 4);
-    ENS(w.Zt, (size_t)w.cap * w.z_max * 4); ENS(w.msg, (size_t)w.cap * HS * 4);
+    if (h->cfg.conv_kernel != 4) {
+      ENS(w.H1, (size_t)w.cap * KP * 4);
+      if (h->cfg.conv_kernel == 1) ENS(w.H1lo, (size_t)w.cap * KP * 4);
+      ENS(w.Zt, (size_t)w.cap * w.z_max * 4);
+    }
+    ENS(w.msg, (size_t)w.cap * HS * 4);
   }
   for (int m = 0; m < 6; ++m) ENS(h->pre[m], (size_t)b.B * NSC * 4);
   ENS(h->h_lig, (size_t)b.N_l * HS * 4); ENS(h->h_atom, (size_t)b.N_a * HS * 4);
@@ -195,7 +200,11 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
-  if (h->cfg.conv_kernel == 0) {
+  if (h->cfg.conv_kernel == 4) {
+    FusedExtra F{};
+    for (int i = 0; i < L.n; ++i) { F.W1hi[i] = X.W1hi[i]; F.W1lo[i] = X.W1lo[i]; F.W2lo[i] = X.W2_lo[i]; F.w2_rows[i] = X.w2_rows[i]; }
+    rc = launch_conv_fused(L, F, h->tp_grid, st);
+  } else if (h->cfg.conv_kernel == 0) {
     k_conv_tp_simt<<<h->n_sms, TP_THREADS, TP_SMEM, st>>>(L);
   } else {
     rc = launch_conv_tc(L, X, h->cfg.conv_kernel, h->tp_grid, st);
@@ -210,12 +219,13 @@ ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* ta
                    const int* bonds, int sh_stride, TcExtra& X, int slot) {
   ConvArgs C{};
   X.H1_lo[slot] = w.H1lo.as<float>(); X.W2_lo[slot] = h->convw[widx].W2lo;
+  X.W1hi[slot] = h->convw[widx].W1hi; X.W1lo[slot] = h->convw[widx].W1lo;
   X.h1_rows[slot] = (uint64_t)w.cap; X.w2_rows[slot] = (uint64_t)h->convw[widx].n_cols;
   C.n_edges = w.seg.as<int>() + w.T; C.es = w.es.as<int>(); C.ed = w.ed.as<int>();
   C.emb = w.emb.as<float>(); C.sh = w.sh.as<float>(); C.sh_stride = sh_stride;
   C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode; C.plan = plan;
   C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1;
-  C.W2p = (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3) ? h->convw[widx].W2hi : h->convw[widx].W2p;
+  C.W2p = (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel >= 3) ? h->convw[widx].W2hi : h->convw[widx].W2p;
   C.H1 = w.H1.as<float>(); C.H1_lo = (h->cfg.conv_kernel == 1) ? w.H1lo.as<float>() : nullptr;
   C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
   return C;
@@ -279,8 +289,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9, X, 1);     // atom
     L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9, X, 2);     // al: target lig, gather atom
     L.c[3] = conv_args(h, h->cw[3], 3 * 6 + l, plan, ha, hl, 0, nullptr, 9, X, 3);     // la: target atom, gather lig
-    k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
-    h->launches += 1;
+    if (h->cfg.conv_kernel != 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
     if ((rc = launch_tp(h, L, X, st))) return rc;
     NodeUpdateArgs U{};
     U.plan = plan;
@@ -322,8 +331,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     TcExtra X{};
     L.n = 1;
     L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8, X, 0);
-    k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
-    h->launches += 1;
+    if (h->cfg.conv_kernel != 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
     if ((rc = launch_tp(h, L, X, st))) return rc;
     TorHeadArgs T{};
     T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
@@ -471,7 +479,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
   CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
   CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
-  if (conv_tc_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  if (conv_tc_init() || conv_fused_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
   h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
   return B200_OK;
 }
@@ -491,6 +499,7 @@ void b200dock_destroy(B200Handle* h) {
   for (void* p : h->plan_allocs) cudaFree(p);
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_w2split) cudaFree(h->d_w2split);
+  if (h->d_w1p) cudaFree(h->d_w1p);
   for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -521,7 +530,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     if (((uintptr_t)w.W2p & 15) != 0) FAIL(B200_ERR_INVALID, "conv record is not 16-byte aligned");
     w.n_cols = P.n_cols;
   }
-  if (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
+  if (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel >= 3) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
     size_t tot = 0;
     for (int i = 0; i < 26; ++i) tot += (size_t)h->convw[i].n_cols * KP;
     if (h->d_w2split) CK(cudaFree(h->d_w2split));
@@ -533,6 +542,17 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
       k_split_tf32<<<148 * 4, 256>>>(h->convw[i].W2p, n, hi, lo);
       h->convw[i].W2hi = hi; h->convw[i].W2lo = lo;
       pos += n;
+    }
+    CK(cudaDeviceSynchronize());
+  }
+  if (h->cfg.conv_kernel == 4) {   // first FC layer packed K-major with the bias column, TF32 hi/lo
+    const size_t n1 = (size_t)192 * KP;
+    if (h->d_w1p) CK(cudaFree(h->d_w1p));
+    CK(cudaMalloc((void**)&h->d_w1p, 26 * 2 * n1 * sizeof(float) + 1024));
+    for (int i = 0; i < 26; ++i) {
+      float* hi = h->d_w1p + (size_t)i * 2 * n1; float* lo = hi + n1;
+      k_build_w1p<<<120, 256>>>(h->convw[i].W1t, h->convw[i].b1, hi, lo);
+      h->convw[i].W1hi = hi; h->convw[i].W1lo = lo;
     }
     CK(cudaDeviceSynchronize());
   }

@@ -42,6 +42,7 @@ struct ConvW {                  // views into the device weight blob
   const float *W1t, *b1, *W2p; LnParams ln;
   const float *W2hi = nullptr, *W2lo = nullptr; int n_cols = 0;
   const float *W1hi = nullptr, *W1lo = nullptr;
+  const __half *W1h16 = nullptr, *W1l16 = nullptr, *W2h16 = nullptr, *W2l16 = nullptr; float inv_s1 = 1.f, inv_s2 = 1.f;
 };
 
 }  // namespace
@@ -54,7 +55,7 @@ struct B200Handle {
   DevPlan dplans[B200_N_PLANS];
   std::vector<void*> plan_allocs;
   int* d_tor_cg_ijk = nullptr; float* d_tor_cg_val = nullptr;
-  float* d_blob = nullptr; float* d_w2split = nullptr; float* d_w1p = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
+  float* d_blob = nullptr; float* d_w2split = nullptr; float* d_w1p = nullptr; __half* d_w16 = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
   ConvW convw[26];
   // workspace
   ConvWs cw[6];
@@ -130,7 +131,7 @@ int setup_workspace(B200Handle* h, const B200Batch& b) {
     ENS(w.es, (size_t)w.cap * 4); ENS(w.ed, (size_t)w.cap * 4);
     if (c == 0) ENS(w.eaux, (size_t)w.cap * 4);
     ENS(w.emb, (size_t)w.cap * NSC * 4); ENS(w.sh, (size_t)w.cap * 9 * 4);
-    if (h->cfg.conv_kernel != 4) {
+    if (h->cfg.conv_kernel < 4) {
       ENS(w.H1, (size_t)w.cap * KP * 4);
       if (h->cfg.conv_kernel == 1) ENS(w.H1lo, (size_t)w.cap * KP * 4);
       ENS(w.Zt, (size_t)w.cap * w.z_max * 4);
@@ -200,7 +201,14 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
-  if (h->cfg.conv_kernel == 4) {
+  if (h->cfg.conv_kernel == 5) {
+    Fused16Extra F{};
+    for (int i = 0; i < L.n; ++i) {
+      F.W1hi[i] = X.W1h16[i]; F.W1lo[i] = X.W1l16[i]; F.W2hi[i] = X.W2h16[i]; F.W2lo[i] = X.W2l16[i];
+      F.w2_rows[i] = X.w2_rows[i] + 96;
+    }
+    rc = launch_conv_fused16(L, F, h->tp_grid, st);
+  } else if (h->cfg.conv_kernel == 4) {
     FusedExtra F{};
     for (int i = 0; i < L.n; ++i) { F.W1hi[i] = X.W1hi[i]; F.W1lo[i] = X.W1lo[i]; F.W2lo[i] = X.W2_lo[i]; F.w2_rows[i] = X.w2_rows[i]; }
     rc = launch_conv_fused(L, F, h->tp_grid, st);
@@ -220,12 +228,15 @@ ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* ta
   ConvArgs C{};
   X.H1_lo[slot] = w.H1lo.as<float>(); X.W2_lo[slot] = h->convw[widx].W2lo;
   X.W1hi[slot] = h->convw[widx].W1hi; X.W1lo[slot] = h->convw[widx].W1lo;
+  X.W1h16[slot] = h->convw[widx].W1h16; X.W1l16[slot] = h->convw[widx].W1l16;
+  X.W2h16[slot] = h->convw[widx].W2h16; X.W2l16[slot] = h->convw[widx].W2l16;
   X.h1_rows[slot] = (uint64_t)w.cap; X.w2_rows[slot] = (uint64_t)h->convw[widx].n_cols;
   C.n_edges = w.seg.as<int>() + w.T; C.es = w.es.as<int>(); C.ed = w.ed.as<int>();
   C.emb = w.emb.as<float>(); C.sh = w.sh.as<float>(); C.sh_stride = sh_stride;
   C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode; C.plan = plan;
   C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1;
-  C.W2p = (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel >= 3) ? h->convw[widx].W2hi : h->convw[widx].W2p;
+  C.W2p = (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3 || h->cfg.conv_kernel == 4) ? h->convw[widx].W2hi : h->convw[widx].W2p;
+  C.inv_s1 = h->convw[widx].inv_s1; C.inv_s2 = h->convw[widx].inv_s2;
   C.H1 = w.H1.as<float>(); C.H1_lo = (h->cfg.conv_kernel == 1) ? w.H1lo.as<float>() : nullptr;
   C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
   return C;
@@ -289,7 +300,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9, X, 1);     // atom
     L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9, X, 2);     // al: target lig, gather atom
     L.c[3] = conv_args(h, h->cw[3], 3 * 6 + l, plan, ha, hl, 0, nullptr, 9, X, 3);     // la: target atom, gather lig
-    if (h->cfg.conv_kernel != 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
+    if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
     if ((rc = launch_tp(h, L, X, st))) return rc;
     NodeUpdateArgs U{};
     U.plan = plan;
@@ -331,7 +342,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     TcExtra X{};
     L.n = 1;
     L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8, X, 0);
-    if (h->cfg.conv_kernel != 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
+    if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
     if ((rc = launch_tp(h, L, X, st))) return rc;
     TorHeadArgs T{};
     T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
@@ -500,6 +511,7 @@ void b200dock_destroy(B200Handle* h) {
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_w2split) cudaFree(h->d_w2split);
   if (h->d_w1p) cudaFree(h->d_w1p);
+  if (h->d_w16) cudaFree(h->d_w16);
   for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -530,7 +542,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     if (((uintptr_t)w.W2p & 15) != 0) FAIL(B200_ERR_INVALID, "conv record is not 16-byte aligned");
     w.n_cols = P.n_cols;
   }
-  if (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel >= 3) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
+  if (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3 || h->cfg.conv_kernel == 4) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
     size_t tot = 0;
     for (int i = 0; i < 26; ++i) tot += (size_t)h->convw[i].n_cols * KP;
     if (h->d_w2split) CK(cudaFree(h->d_w2split));
@@ -555,6 +567,36 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
       h->convw[i].W1hi = hi; h->convw[i].W1lo = lo;
     }
     CK(cudaDeviceSynchronize());
+  }
+  if (h->cfg.conv_kernel == 5) {   // fp16 hi/lo copies of W1p / W2p with exact power-of-two scales
+    size_t tot = 0;
+    for (int i = 0; i < 26; ++i) tot += ((size_t)h->convw[i].n_cols + 96 + 192) * KH;
+    if (h->d_w16) CK(cudaFree(h->d_w16));
+    CK(cudaMalloc((void**)&h->d_w16, 2 * tot * sizeof(__half) + 1024));
+    float* tmp = nullptr; float* d_max = nullptr;
+    CK(cudaMalloc((void**)&tmp, (size_t)192 * KP * sizeof(float)));
+    CK(cudaMalloc((void**)&d_max, 2 * sizeof(float)));
+    size_t pos = 0;
+    for (int i = 0; i < 26; ++i) {
+      ConvW& w = h->convw[i];
+      const size_t n2 = (size_t)w.n_cols * KP, r2 = (size_t)w.n_cols + 96;
+      k_build_w1p_f32<<<120, 256>>>(w.W1t, w.b1, tmp);
+      CK(cudaMemset(d_max, 0, 2 * sizeof(float)));
+      k_absmax<<<148, 256>>>(tmp, (size_t)192 * KP, d_max);
+      k_absmax<<<148 * 4, 256>>>(w.W2p, n2, d_max + 1);
+      float mx[2];
+      CK(cudaMemcpy(mx, d_max, sizeof mx, cudaMemcpyDeviceToHost));
+      auto scale_of = [](float m) { int ex; frexpf(m > 0 ? m : 1.0f, &ex); return ldexpf(1.0f, 10 - ex); };   // max -> [2^9, 2^10)
+      const float s1 = scale_of(mx[0]), s2 = scale_of(mx[1]);
+      __half* h1 = h->d_w16 + pos; __half* l1 = h1 + (size_t)192 * KH;
+      __half* h2 = l1 + (size_t)192 * KH; __half* l2 = h2 + r2 * KH;
+      k_build_w16<<<148, 256>>>(tmp, 192, 192, s1, h1, l1);
+      k_build_w16<<<148 * 4, 256>>>(w.W2p, w.n_cols, (int)r2, s2, h2, l2);
+      w.W1h16 = h1; w.W1l16 = l1; w.W2h16 = h2; w.W2l16 = l2; w.inv_s1 = 1.0f / s1; w.inv_s2 = 1.0f / s2;
+      pos += 2 * (size_t)192 * KH + 2 * r2 * KH;
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaFree(tmp)); CK(cudaFree(d_max));
   }
   h->weights = true;
   return B200_OK;

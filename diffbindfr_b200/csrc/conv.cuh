@@ -60,6 +60,7 @@ struct ConvArgs {
   float* H1_lo;             // optional: H1 - tf32(H1) for the 3xTF32 tensor-core mode (H1 then holds tf32(H1))
   float* Zt;                // [tiles][z_numel][128]
   float* msg;               // [E_pad][HS]
+  float inv_s1, inv_s2;     // fp16 mode: inverse power-of-two scales of the packed W1 / W2
 };
 struct ConvLaunch { ConvArgs c[4]; int n; };
 

@@ -10,6 +10,7 @@
 // Neither H1 nor the [E, weight_numel] weights nor Z are ever written to global memory
 // (the reference materialises [E, 7776] fp32 per conv).
 #pragma once
+#include <cuda_fp16.h>
 #include "conv_tc.cuh"
 
 #define F_NST 5
@@ -31,6 +32,16 @@ __global__ void k_build_w1p(const float* __restrict__ W1t, const float* __restri
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
     float h = __uint_as_float(hb);
     hi[idx] = h; lo[idx] = v - h;
+  }
+}
+
+// fp32 W1p[192][160] (no split), source for the fp16 packing
+__global__ void k_build_w1p_f32(const float* __restrict__ W1t, const float* __restrict__ b1, float* __restrict__ out) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 192 * KP; idx += gridDim.x * blockDim.x) {
+    int j = idx / KP, k = idx % KP;
+    float v = 0.0f;
+    if (j < 144) v = (k < 144) ? W1t[k * 144 + j] : (k == 144 ? b1[j] : 0.0f);
+    out[idx] = v;
   }
 }
 
@@ -346,10 +357,418 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused(ConvLaunch L, cons
   }
 }
 
+
+namespace tc {
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // fp16 x fp16 -> fp32
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// power-of-two scale that maps a row maximum into [2^9, 2^10): keeps fp16 hi/lo splits normal
+__device__ __forceinline__ float row_scale(float mx) {
+  int ex = ((__float_as_int(mx) >> 23) & 0xff) - 127;
+  return __int_as_float((127 + 9 - ex) << 23);
+}
+// 64 fp32 values -> fp16 hi / lo pairs -> 32 + 32 tensor-memory columns (element 2c in the low half of column c)
+__device__ __forceinline__ void pack_store_f16(uint32_t addr_hi, uint32_t addr_lo, const float* v) {
+  float ph[32], pl[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    __half h0 = __float2half_rn(v[2 * c]), h1 = __float2half_rn(v[2 * c + 1]);
+    __half l0 = __float2half_rn(v[2 * c] - __half2float(h0)), l1 = __float2half_rn(v[2 * c + 1] - __half2float(h1));
+    ph[c] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
+    pl[c] = __uint_as_float((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16));
+  }
+  tmem_st32(addr_hi, ph);
+  tmem_st32(addr_lo, pl);
+}
+}  // namespace tc
+
+// MODE 5: the fused kernel with FP16 hi/lo splits (3 x kind::f16 MMAs per K-step, K = 192 halves): same
+// error-compensation scheme, twice the tensor throughput and ~60 % of the W streaming of the TF32 variant.
+// fp16's narrow exponent is handled by exact power-of-two scaling: per conv for W1/W2 (max -> [2^9,2^10)),
+// per edge row for xin and H1 (each thread owns its row, so the scale stays thread-local and is undone in
+// the fold / in the ReLU epilogue).
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
+  constexpr int BN = F_BN, NST = F_NST;
+  constexpr int KATOMS = 3;                      // K = 192 halves = 3 swizzle atoms of 64 fp16
+  constexpr int ACOLS = 96;                      // tensor-memory columns of one (hi or lo) A term
+  constexpr int D0 = 192;                        // accumulator buffers at columns [192,288) and [288,384)
+  constexpr uint32_t B_PART = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = base;                                              // [NST][2][96 x 128 B]
+  float* x1s = reinterpret_cast<float*>(sB + (size_t)NST * 2 * B_PART);   // [128][169] per-edge scratch rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x1s + 128 * F_X1S);
+  uint64_t* x_full = bars;            uint64_t* h_full = bars + 1;  uint64_t* a_empty = bars + 2;
+  uint64_t* b_full = bars + 3;        uint64_t* b_empty = bars + 3 + NST;
+  uint64_t* d_full = bars + 3 + 2 * NST;  uint64_t* d_empty = d_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(x_full, 128); tc::mbar_init(h_full, 128); tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < NST; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0)
+      for (int ci = 0; ci < L.n; ++ci) {
+        tc::prefetch_tmap(&maps.w2[ci]); tc::prefetch_tmap(&maps.w2_lo[ci]);
+        tc::prefetch_tmap(&maps.w1[ci]); tc::prefetch_tmap(&maps.w1_lo[ci]);
+      }
+    __syncwarp();
+    tc::Phase st;
+    int tiles_before = 0;
+    for (int ci = 0; ci < L.n; ++ci) {
+      const ConvArgs& C = L.c[ci];
+      const DevPlan& P = c_plans[C.plan];
+      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
+      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
+      tiles_before += ntile;
+      for (int tile = first; tile < ntile; tile += gridDim.x) {
+        for (int unit = -2; unit < P.n_chunks; ++unit) {
+          const CUtensorMap* mh = unit < 0 ? &maps.w1[ci] : &maps.w2[ci];
+          const CUtensorMap* ml = unit < 0 ? &maps.w1_lo[ci] : &maps.w2_lo[ci];
+          const int row0 = unit < 0 ? (unit + 2) * BN : P.chunk_col[unit];
+          for (int ka = 0; ka < KATOMS; ++ka) {
+            tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
+            if (tc::elect_one()) {
+              tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
+              uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
+              tc::tma_load_2d(dst, mh, ka * 64, row0, &b_full[st.idx]);
+              tc::tma_load_2d(dst + B_PART, ml, ka * 64, row0, &b_full[st.idx]);
+            }
+            __syncwarp();
+            tc::advance(st, NST);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    tc::Phase st, db;
+    uint32_t xpar = 0, hpar = 0;
+    int tiles_before = 0;
+    for (int ci = 0; ci < L.n; ++ci) {
+      const ConvArgs& C = L.c[ci];
+      const DevPlan& P = c_plans[C.plan];
+      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
+      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
+      tiles_before += ntile;
+      for (int tile = first; tile < ntile; tile += gridDim.x) {
+        tc::mbar_wait(x_full, xpar);
+        xpar ^= 1;
+        tc::fence_after();
+        for (int unit = -2; unit < P.n_chunks; ++unit) {
+          if (unit == 0) {                              // H1 must be in tensor memory before the W2 units
+            tc::mbar_wait(h_full, hpar);
+            hpar ^= 1;
+            tc::fence_after();
+          }
+          const int N = unit == -2 ? 96 : (unit == -1 ? 48 : P.chunk_n[unit]);
+          tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
+          tc::fence_after();
+          const uint32_t idesc = tc::make_idesc_f16(128, N);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(D0 + db.idx * BN);
+          for (int ka = 0; ka < KATOMS; ++ka) {
+            tc::mbar_wait(&b_full[st.idx], st.par);
+            tc::fence_after();
+            const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * 2 * B_PART);
+            const uint64_t dh = tc::make_desc(b_hi), dl = tc::make_desc(b_hi + B_PART);
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) {
+                const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + ACOLS;
+                tc::mma_f16_ts(d_tmem, a_lo, dh + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
+                tc::mma_f16_ts(d_tmem, a_hi, dl + (uint64_t)(k8 * 2), idesc, 1u);
+                tc::mma_f16_ts(d_tmem, a_hi, dh + (uint64_t)(k8 * 2), idesc, 1u);
+              }
+              tc::mma_commit(&b_empty[st.idx]);
+              if (ka == KATOMS - 1) {
+                tc::mma_commit(&d_full[db.idx]);
+                if (unit + 1 == P.n_chunks) tc::mma_commit(a_empty);
+              }
+            }
+            __syncwarp();
+            tc::advance(st, NST);
+          }
+          tc::advance(db, 2);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================== gather / H1 / epilogue warps (thread = edge)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* xrow = x1s + row * F_X1S;
+    tc::Phase db;
+    uint32_t apar = 0;
+    int tiles_before = 0;
+    for (int ci = 0; ci < L.n; ++ci) {
+      const ConvArgs& C = L.c[ci];
+      const DevPlan& P = c_plans[C.plan];
+      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
+      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
+      tiles_before += ntile;
+      for (int tile = first; tile < ntile; tile += gridDim.x) {
+        const int e = tile * TILE_E + row;
+        const int s = C.es[e], d = C.ed[e];
+        float sx = 1.0f, shh = 1.0f;
+        // ---- 1. xin -> tensor memory
+        tc::mbar_wait(a_empty, apar ^ 1);
+        apar ^= 1;
+        tc::fence_after();
+        {
+          const float4* pe = reinterpret_cast<const float4*>(C.emb + (size_t)e * NSC);
+          const float4* pa = reinterpret_cast<const float4*>(C.tabA + (size_t)(C.mode == 0 ? s : d) * HS);
+          const float4* pb0; const float4* pb1 = nullptr;
+          if (C.mode == 0) pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
+          else {
+            pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
+            pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
+          }
+          float mx = 1.0f;                               // the ones column
+#pragma unroll 4
+          for (int k4 = 0; k4 < 36; ++k4) {
+            float4 f;
+            if (k4 < 12) f = __ldg(pe + k4);
+            else if (k4 < 24) f = __ldg(pa + (k4 - 12));
+            else {
+              f = __ldg(pb0 + (k4 - 24));
+              if (pb1) { float4 f2 = __ldg(pb1 + (k4 - 24)); f.x += f2.x; f.y += f2.y; f.z += f2.z; f.w += f2.w; }
+            }
+            xrow[4 * k4] = f.x; xrow[4 * k4 + 1] = f.y; xrow[4 * k4 + 2] = f.z; xrow[4 * k4 + 3] = f.w;
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w))));
+          }
+          sx = tc::row_scale(mx);
+#pragma unroll 1
+          for (int g = 0; g < 3; ++g) {
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const int k = g * 64 + j;
+              v[j] = (k < 144) ? xrow[k] * sx : (k == 144 ? sx : 0.0f);
+            }
+            tc::pack_store_f16(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(ACOLS + g * 32), v);
+          }
+          tc::tmem_wait_st();
+          tc::fence_before();
+          tc::mbar_arrive(x_full);
+        }
+        // ---- x1 row -> per-thread scratch, edge harmonics -> registers
+        {
+          const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
+          const int nq = (P.in_dim + 3) >> 2;
+          for (int qq = 0; qq < nq; ++qq) {
+            float4 f = __ldg(px + qq);
+            xrow[4 * qq] = f.x; xrow[4 * qq + 1] = f.y; xrow[4 * qq + 2] = f.z; xrow[4 * qq + 3] = f.w;
+          }
+        }
+        float shv[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
+        // ---- 3. D1 -> relu -> H1 hi/lo -> tensor memory
+        {
+          tc::Phase p0 = db; tc::advance(db, 2);
+          tc::Phase p1 = db; tc::advance(db, 2);
+          tc::mbar_wait(&d_full[p0.idx], p0.par);
+          tc::mbar_wait(&d_full[p1.idx], p1.par);
+          tc::fence_after();
+          const uint32_t t0 = lane_base + (uint32_t)(D0 + p0.idx * BN), t1 = lane_base + (uint32_t)(D0 + p1.idx * BN);
+          const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
+          float mx = 1.0f;
+#pragma unroll 1
+          for (int g = 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
+            float v[16];
+            tc::tmem_ld16(g < 6 ? t0 + g * 16 : t1 + (g - 6) * 16, v);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j] * inv1);
+          }
+          shh = tc::row_scale(mx);
+          const float sc1 = inv1 * shh;
+#pragma unroll 1
+          for (int g = 0; g < 3; ++g) {                  // pass 2: relu, scale, fp16 hi/lo, store
+            float v[64];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int j0 = g * 64 + c * 16;            // output channel of v[c*16]
+              if (j0 < 96) tc::tmem_ld16(t0 + j0, v + c * 16);
+              else if (j0 < 144) tc::tmem_ld16(t1 + (j0 - 96), v + c * 16);
+            }
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+              const int k = g * 64 + j;
+              v[j] = (k < 144) ? fmaxf(v[j], 0.0f) * sc1 : (k == 144 ? shh : 0.0f);
+            }
+            tc::pack_store_f16(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(ACOLS + g * 32), v);
+          }
+          tc::tmem_wait_st();
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) { tc::mbar_arrive(&d_empty[p0.idx]); tc::mbar_arrive(&d_empty[p1.idx]); }
+          tc::mbar_arrive(h_full);
+        }
+        // ---- 5. W2 units: fold with Z computed on the fly
+        float* mrow = C.msg + (size_t)e * HS;
+        float o[48];
+#pragma unroll
+        for (int i = 0; i < 48; ++i) o[i] = 0.0f;
+        int cur_path = -1;
+        float M[9];
+        for (int ch = 0; ch < P.n_chunks; ++ch) {
+          const int col0 = P.chunk_col[ch], N = P.chunk_n[ch];
+          const int pidx = P.chunk_path[ch];
+          const B200Path pa = P.paths[pidx];
+          const int d1 = 2 * pa.l1 + 1;
+          if (pidx != cur_path) {                        // M[i][k] = sum_j C[i][j][k] sh[j]
+            cur_path = pidx;
+            const float* cg = c_cg_dense[C.plan][pidx];
+            const int d2 = 2 * pa.l2 + 1;
+#pragma unroll
+            for (int ik = 0; ik < 9; ++ik) M[ik] = 0.0f;
+            for (int j = 0; j < d2; ++j) {
+              const float sj = shv[0] * (pa.in2_off + j == 0) + shv[1] * (pa.in2_off + j == 1) + shv[2] * (pa.in2_off + j == 2) +
+                               shv[3] * (pa.in2_off + j == 3) + shv[4] * (pa.in2_off + j == 4) + shv[5] * (pa.in2_off + j == 5) +
+                               shv[6] * (pa.in2_off + j == 6) + shv[7] * (pa.in2_off + j == 7) + shv[8] * (pa.in2_off + j == 8);
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) M[i * 3 + k] = fmaf(cg[(i * 5 + j) * 3 + k], sj, M[i * 3 + k]);
+            }
+          }
+          const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
+          const float* xp = xrow + pa.in1_off + u0 * d1;
+          tc::mbar_wait(&d_full[db.idx], db.par);
+          tc::fence_after();
+          const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
+          const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
+          if (pa.Wd == 48) {
+            for (int uu = 0; uu < nu; ++uu) {
+              float v[48];
+              tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
+              float z = xp[uu * d1] * M[0];
+              if (d1 == 3) z = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], z));
+              z *= zs;
+              tc::tmem_wait_ld();
+#pragma unroll
+              for (int w = 0; w < 48; ++w) o[w] = fmaf(v[w], z, o[w]);
+            }
+          } else {
+            for (int uu = 0; uu < nu; ++uu) {
+              float v[12];
+              tc::tmem_ld4(taddr + uu * 12, v); tc::tmem_ld4(taddr + uu * 12 + 4, v + 4); tc::tmem_ld4(taddr + uu * 12 + 8, v + 8);
+              const float x0 = xp[uu * d1];
+              float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
+              if (d1 == 3) {
+                const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
+                z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
+              }
+              z0 *= zs; z1 *= zs; z2 *= zs;
+              tc::tmem_wait_ld();
+#pragma unroll
+              for (int w = 0; w < 12; ++w) {
+                o[w * 3] = fmaf(v[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(v[w], z1, o[w * 3 + 1]);
+                o[w * 3 + 2] = fmaf(v[w], z2, o[w * 3 + 2]);
+              }
+            }
+          }
+          tc::fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&d_empty[db.idx]);
+          tc::advance(db, 2);
+          bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
+          if (last) {
+            const int nout = (pa.Wd == 48) ? 48 : 36;
+#pragma unroll
+            for (int i = 0; i < 48; i += 4) {
+              if (i < nout) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+              o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 struct FusedExtra { const float* W1hi[4]; const float* W1lo[4]; const float* W2lo[4]; uint64_t w2_rows[4]; };
 
 static inline int conv_fused_init() {
-  return cudaFuncSetAttribute(k_conv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) == cudaSuccess ? 0 : 1;
+  if (cudaFuncSetAttribute(k_conv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) != cudaSuccess) return 1;
+  return cudaFuncSetAttribute(k_conv_fused16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) == cudaSuccess ? 0 : 1;
+}
+
+#define KH 192   // fp16 K (halves), padded to 3 swizzle atoms
+
+// fp32 [rows][160] (K-major, packed W2p / W1p) -> fp16 hi / lo [rows_out][192] scaled by `scale`
+__global__ void k_build_w16(const float* __restrict__ src, int rows, int rows_out, float scale, __half* __restrict__ hi,
+                            __half* __restrict__ lo) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)rows_out * KH; idx += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(idx / KH), k = (int)(idx % KH);
+    float v = (j < rows && k < KP) ? src[(size_t)j * KP + k] * scale : 0.0f;
+    __half h = __float2half_rn(v);
+    hi[idx] = h; lo[idx] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+__global__ void k_absmax(const float* __restrict__ src, size_t n, float* __restrict__ out) {
+  float m = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // non-negative floats order as ints
+}
+
+static inline int tc_make_map16(CUtensorMap* m, const void* ptr, uint64_t rows, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {KH, rows};
+  cuuint64_t gstr[1] = {KH * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+struct Fused16Extra { const void* W1hi[4]; const void* W1lo[4]; const void* W2hi[4]; const void* W2lo[4]; uint64_t w2_rows[4]; };
+
+static inline int launch_conv_fused16(const ConvLaunch& L, const Fused16Extra& X, int grid, cudaStream_t st) {
+  if (!g_encode) return 1;
+  FusedMaps maps;
+  memset(&maps, 0, sizeof maps);
+  for (int i = 0; i < L.n; ++i) {
+    if (tc_make_map16(&maps.w2[i], X.W2hi[i], X.w2_rows[i], F_BN)) return 2;
+    if (tc_make_map16(&maps.w2_lo[i], X.W2lo[i], X.w2_rows[i], F_BN)) return 3;
+    if (tc_make_map16(&maps.w1[i], X.W1hi[i], 192, F_BN)) return 4;
+    if (tc_make_map16(&maps.w1_lo[i], X.W1lo[i], 192, F_BN)) return 5;
+  }
+  k_conv_fused16<<<grid, TC_THREADS, F_SMEM, st>>>(L, maps);
+  return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }
 
 static inline int launch_conv_fused(const ConvLaunch& L, const FusedExtra& X, int grid, cudaStream_t st) {

@@ -599,6 +599,7 @@ static inline int tc_make_map(CUtensorMap* m, const float* ptr, uint64_t rows, u
 struct TcExtra {               // per conv: lo copies and row counts
   const float* H1_lo[4]; const float* W2_lo[4]; uint64_t h1_rows[4]; uint64_t w2_rows[4];
   const float* W1hi[4]; const float* W1lo[4];
+  const void* W1h16[4]; const void* W1l16[4]; const void* W2h16[4]; const void* W2l16[4];
 };
 
 static inline int launch_conv_tc(const ConvLaunch& L, const TcExtra& X, int mode, int n_sms, cudaStream_t st) {

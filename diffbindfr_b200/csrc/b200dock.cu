@@ -205,7 +205,7 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t
     Fused16Extra F{};
     for (int i = 0; i < L.n; ++i) {
       F.W1hi[i] = X.W1h16[i]; F.W1lo[i] = X.W1l16[i]; F.W2hi[i] = X.W2h16[i]; F.W2lo[i] = X.W2l16[i];
-      F.w2_rows[i] = X.w2_rows[i] + 96;
+      F.w2_rows[i] = X.w2_rows[i] + 144;
     }
     rc = launch_conv_fused16(L, F, h->tp_grid, st);
   } else if (h->cfg.conv_kernel == 4) {
@@ -570,7 +570,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
   }
   if (h->cfg.conv_kernel == 5) {   // fp16 hi/lo copies of W1p / W2p with exact power-of-two scales
     size_t tot = 0;
-    for (int i = 0; i < 26; ++i) tot += ((size_t)h->convw[i].n_cols + 96 + 192) * KH;
+    for (int i = 0; i < 26; ++i) tot += ((size_t)h->convw[i].n_cols + 144 + 192) * KH;
     if (h->d_w16) CK(cudaFree(h->d_w16));
     CK(cudaMalloc((void**)&h->d_w16, 2 * tot * sizeof(__half) + 1024));
     float* tmp = nullptr; float* d_max = nullptr;
@@ -579,7 +579,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     size_t pos = 0;
     for (int i = 0; i < 26; ++i) {
       ConvW& w = h->convw[i];
-      const size_t n2 = (size_t)w.n_cols * KP, r2 = (size_t)w.n_cols + 96;
+      const size_t n2 = (size_t)w.n_cols * KP, r2 = (size_t)w.n_cols + 144;
       k_build_w1p_f32<<<120, 256>>>(w.W1t, w.b1, tmp);
       CK(cudaMemset(d_max, 0, 2 * sizeof(float)));
       k_absmax<<<148, 256>>>(tmp, (size_t)192 * KP, d_max);

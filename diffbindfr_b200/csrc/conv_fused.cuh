@@ -17,7 +17,10 @@
 #define F_BN 96
 #define F_D0 320
 #define F_X1S 169
+#define F16_BN 144                   // fp16 mode: unit width (columns) and ring depth
+#define F16_NST 3
 constexpr size_t F_SMEM = 1024 + (size_t)F_NST * 2 * F_BN * 128 + (size_t)128 * F_X1S * 4 + 256;
+constexpr size_t F16_SMEM = 1024 + (size_t)F16_NST * 2 * F16_BN * 128 + (size_t)128 * F_X1S * 4 + 256;
 
 struct FusedMaps { CUtensorMap w2[4], w2_lo[4], w1[4], w1_lo[4]; };
 
@@ -395,7 +398,7 @@ __device__ __forceinline__ void pack_store_f16(uint32_t addr_hi, uint32_t addr_l
 // per edge row for xin and H1 (each thread owns its row, so the scale stays thread-local and is undone in
 // the fold / in the ReLU epilogue).
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
-  constexpr int BN = F_BN, NST = F_NST;
+  constexpr int BN = F16_BN, NST = F16_NST;
   constexpr int KATOMS = 3;                      // K = 192 halves = 3 swizzle atoms of 64 fp16
   constexpr int ACOLS = 96;                      // tensor-memory columns of one (hi or lo) A term
   constexpr int D0 = 192;                        // accumulator buffers at columns [192,288) and [288,384)
@@ -443,10 +446,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
       int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
       tiles_before += ntile;
       for (int tile = first; tile < ntile; tile += gridDim.x) {
-        for (int unit = -2; unit < P.n_chunks; ++unit) {
+        for (int unit = -1; unit < P.n_chunks; ++unit) {
           const CUtensorMap* mh = unit < 0 ? &maps.w1[ci] : &maps.w2[ci];
           const CUtensorMap* ml = unit < 0 ? &maps.w1_lo[ci] : &maps.w2_lo[ci];
-          const int row0 = unit < 0 ? (unit + 2) * BN : P.chunk_col[unit];
+          const int row0 = unit < 0 ? 0 : P.chunk_col[unit];
           for (int ka = 0; ka < KATOMS; ++ka) {
             tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
             if (tc::elect_one()) {
@@ -463,8 +466,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
     }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
-    tc::Phase st, db;
-    uint32_t xpar = 0, hpar = 0;
+    // Every unit consumes exactly KATOMS == NST ring stages, so stage index == K-atom index and the
+    // shared-memory descriptors are loop invariant: all per-stage setup is hoisted out of the issue loop.
+    static_assert(F16_NST == 3, "stage == k-atom mapping");
+    tc::Phase db;
+    uint32_t xpar = 0, hpar = 0, bpar = 0;
+    uint64_t dhs[KATOMS], dls[KATOMS];
+#pragma unroll
+    for (int ka = 0; ka < KATOMS; ++ka) {
+      const uint32_t b_hi = tc::smem_u32(sB + (size_t)ka * 2 * B_PART);
+      dhs[ka] = tc::make_desc(b_hi); dls[ka] = tc::make_desc(b_hi + B_PART);
+    }
     int tiles_before = 0;
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
@@ -476,39 +488,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         tc::mbar_wait(x_full, xpar);
         xpar ^= 1;
         tc::fence_after();
-        for (int unit = -2; unit < P.n_chunks; ++unit) {
+        for (int unit = -1; unit < P.n_chunks; ++unit) {
           if (unit == 0) {                              // H1 must be in tensor memory before the W2 units
             tc::mbar_wait(h_full, hpar);
             hpar ^= 1;
             tc::fence_after();
           }
-          const int N = unit == -2 ? 96 : (unit == -1 ? 48 : P.chunk_n[unit]);
-          tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
-          tc::fence_after();
+          const int N = unit < 0 ? 144 : P.chunk_n[unit];
           const uint32_t idesc = tc::make_idesc_f16(128, N);
           const uint32_t d_tmem = tmem_base + (uint32_t)(D0 + db.idx * BN);
+          const bool last_unit = (unit + 1 == P.n_chunks);
+          tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
+          tc::fence_after();
+#pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
-            tc::mbar_wait(&b_full[st.idx], st.par);
+            tc::mbar_wait(&b_full[ka], bpar);
             tc::fence_after();
-            const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * 2 * B_PART);
-            const uint64_t dh = tc::make_desc(b_hi), dl = tc::make_desc(b_hi + B_PART);
             if (tc::elect_one()) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
                 const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + ACOLS;
-                tc::mma_f16_ts(d_tmem, a_lo, dh + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
-                tc::mma_f16_ts(d_tmem, a_hi, dl + (uint64_t)(k8 * 2), idesc, 1u);
-                tc::mma_f16_ts(d_tmem, a_hi, dh + (uint64_t)(k8 * 2), idesc, 1u);
+                tc::mma_f16_ts(d_tmem, a_lo, dhs[ka] + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
+                tc::mma_f16_ts(d_tmem, a_hi, dls[ka] + (uint64_t)(k8 * 2), idesc, 1u);
+                tc::mma_f16_ts(d_tmem, a_hi, dhs[ka] + (uint64_t)(k8 * 2), idesc, 1u);
               }
-              tc::mma_commit(&b_empty[st.idx]);
+              tc::mma_commit(&b_empty[ka]);
               if (ka == KATOMS - 1) {
                 tc::mma_commit(&d_full[db.idx]);
-                if (unit + 1 == P.n_chunks) tc::mma_commit(a_empty);
+                if (last_unit) tc::mma_commit(a_empty);
               }
             }
             __syncwarp();
-            tc::advance(st, NST);
           }
+          bpar ^= 1;
           tc::advance(db, 2);
         }
       }
@@ -588,17 +600,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         // ---- 3. D1 -> relu -> H1 hi/lo -> tensor memory
         {
           tc::Phase p0 = db; tc::advance(db, 2);
-          tc::Phase p1 = db; tc::advance(db, 2);
           tc::mbar_wait(&d_full[p0.idx], p0.par);
-          tc::mbar_wait(&d_full[p1.idx], p1.par);
           tc::fence_after();
-          const uint32_t t0 = lane_base + (uint32_t)(D0 + p0.idx * BN), t1 = lane_base + (uint32_t)(D0 + p1.idx * BN);
+          const uint32_t t0 = lane_base + (uint32_t)(D0 + p0.idx * BN);
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
           float mx = 1.0f;
 #pragma unroll 1
           for (int g = 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
             float v[16];
-            tc::tmem_ld16(g < 6 ? t0 + g * 16 : t1 + (g - 6) * 16, v);
+            tc::tmem_ld16(t0 + g * 16, v);
             tc::tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; ++j) mx = fmaxf(mx, v[j] * inv1);
@@ -611,21 +621,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const int j0 = g * 64 + c * 16;            // output channel of v[c*16]
-              if (j0 < 96) tc::tmem_ld16(t0 + j0, v + c * 16);
-              else if (j0 < 144) tc::tmem_ld16(t1 + (j0 - 96), v + c * 16);
+              if (j0 < 144) tc::tmem_ld16(t0 + j0, v + c * 16);
             }
             tc::tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
-              const int k = g * 64 + j;
-              v[j] = (k < 144) ? fmaxf(v[j], 0.0f) * sc1 : (k == 144 ? shh : 0.0f);
+              const int kk = g * 64 + j;
+              v[j] = (kk < 144) ? fmaxf(v[j], 0.0f) * sc1 : (kk == 144 ? shh : 0.0f);
             }
             tc::pack_store_f16(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(ACOLS + g * 32), v);
           }
           tc::tmem_wait_st();
           tc::fence_before();
           __syncwarp();
-          if (lane == 0) { tc::mbar_arrive(&d_empty[p0.idx]); tc::mbar_arrive(&d_empty[p1.idx]); }
+          if (lane == 0) tc::mbar_arrive(&d_empty[p0.idx]);
           tc::mbar_arrive(h_full);
         }
         // ---- 5. W2 units: fold with Z computed on the fly
@@ -721,7 +730,7 @@ struct FusedExtra { const float* W1hi[4]; const float* W1lo[4]; const float* W2l
 
 static inline int conv_fused_init() {
   if (cudaFuncSetAttribute(k_conv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) != cudaSuccess) return 1;
-  return cudaFuncSetAttribute(k_conv_fused16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) == cudaSuccess ? 0 : 1;
+  return cudaFuncSetAttribute(k_conv_fused16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F16_SMEM) == cudaSuccess ? 0 : 1;
 }
 
 #define KH 192   // fp16 K (halves), padded to 3 swizzle atoms
@@ -762,12 +771,12 @@ static inline int launch_conv_fused16(const ConvLaunch& L, const Fused16Extra& X
   FusedMaps maps;
   memset(&maps, 0, sizeof maps);
   for (int i = 0; i < L.n; ++i) {
-    if (tc_make_map16(&maps.w2[i], X.W2hi[i], X.w2_rows[i], F_BN)) return 2;
-    if (tc_make_map16(&maps.w2_lo[i], X.W2lo[i], X.w2_rows[i], F_BN)) return 3;
-    if (tc_make_map16(&maps.w1[i], X.W1hi[i], 192, F_BN)) return 4;
-    if (tc_make_map16(&maps.w1_lo[i], X.W1lo[i], 192, F_BN)) return 5;
+    if (tc_make_map16(&maps.w2[i], X.W2hi[i], X.w2_rows[i], F16_BN)) return 2;
+    if (tc_make_map16(&maps.w2_lo[i], X.W2lo[i], X.w2_rows[i], F16_BN)) return 3;
+    if (tc_make_map16(&maps.w1[i], X.W1hi[i], 192, F16_BN)) return 4;
+    if (tc_make_map16(&maps.w1_lo[i], X.W1lo[i], 192, F16_BN)) return 5;
   }
-  k_conv_fused16<<<grid, TC_THREADS, F_SMEM, st>>>(L, maps);
+  k_conv_fused16<<<grid, TC_THREADS, F16_SMEM, st>>>(L, maps);
   return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }
 

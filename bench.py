@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfgA")
-    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "4")))
+    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "5")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-poses", type=int, default=2)
     args = ap.parse_args()

@@ -72,6 +72,7 @@ struct B200Handle {
   int n_sms = 148;
   int debug_layers = 6;
   int tp_grid = 148;
+  std::vector<float> cg_dense;
 };
 
 namespace {
@@ -243,9 +244,23 @@ ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* ta
 }
 
 // One evaluation of the score network on device-resident batch + conditioning.
+// The conv plans live in __constant__ memory (one copy per device and module); a handle re-uploads its own
+// tables, stream-ordered, whenever another handle used the device last.
+static B200Handle* g_plan_owner[64] = {nullptr};
+
+int bind_plans(B200Handle* h, cudaStream_t st) {
+  const int dev = h->device & 63;
+  if (g_plan_owner[dev] == h) return B200_OK;
+  CK(cudaMemcpyToSymbolAsync(c_plans, h->dplans, sizeof(DevPlan) * B200_N_PLANS, 0, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyToSymbolAsync(c_cg_dense, h->cg_dense.data(), h->cg_dense.size() * sizeof(float), 0, cudaMemcpyHostToDevice, st));
+  g_plan_owner[dev] = h;
+  return B200_OK;
+}
+
 int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr, float* rot, float* tor, float* sc,
                  cudaStream_t st) {
   if (!h->weights) FAIL(B200_ERR_STATE, "weights not loaded");
+  { int rcb = bind_plans(h, st); if (rcb) return rcb; }
   const float* W = h->d_blob;
   const std::vector<int64_t>& off = h->off;
   // ---- sigma pre-activations
@@ -456,21 +471,20 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
     for (int i = 0; i < B200_MAX_BLOCKS; ++i) d.blocks[i] = s.blocks[i];
     d.n_cg = s.n_cg; d.n_chunks = s.n_chunks;
     int rc;
-    int *ijk, *cc, *cn, *cp; float* val;
+    int* ijk; float* val;
+    if (s.n_chunks > B200_MAX_CHUNKS) FAIL(B200_ERR_INVALID, "too many weight chunks in a conv plan");
     if ((rc = upload(h, s.cg_ijk, (size_t)s.n_cg, &ijk))) return rc;
     if ((rc = upload(h, s.cg_val, (size_t)s.n_cg, &val))) return rc;
-    if ((rc = upload(h, s.chunk_col, (size_t)s.n_chunks, &cc))) return rc;
-    if ((rc = upload(h, s.chunk_n, (size_t)s.n_chunks, &cn))) return rc;
-    if ((rc = upload(h, s.chunk_path, (size_t)s.n_chunks, &cp))) return rc;
-    d.cg_ijk = ijk; d.cg_val = val; d.chunk_col = cc; d.chunk_n = cn; d.chunk_path = cp;
+    d.cg_ijk = ijk; d.cg_val = val;
+    for (int i = 0; i < s.n_chunks; ++i) { d.chunk_col[i] = s.chunk_col[i]; d.chunk_n[i] = s.chunk_n[i]; d.chunk_path[i] = s.chunk_path[i]; }
     // keep host copies for the tensor-core path (chunk tables are read on the host too)
     h->hold_i.emplace_back(s.chunk_col, s.chunk_col + s.n_chunks);
     h->hold_i.emplace_back(s.chunk_n, s.chunk_n + s.n_chunks);
     h->hold_i.emplace_back(s.chunk_path, s.chunk_path + s.n_chunks);
   }
-  CK(cudaMemcpyToSymbol(c_plans, h->dplans, sizeof(DevPlan) * B200_N_PLANS));
   {
-    std::vector<float> dense((size_t)B200_N_PLANS * B200_MAX_PATHS * 45, 0.0f);
+    std::vector<float>& dense = h->cg_dense;
+    dense.assign((size_t)B200_N_PLANS * B200_MAX_PATHS * 45, 0.0f);
     for (int p = 0; p < B200_N_PLANS; ++p) {
       const B200ConvPlan& s = cfg->plans[p];
       for (int q = 0; q < s.n_paths; ++q) {
@@ -482,7 +496,6 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
         }
       }
     }
-    CK(cudaMemcpyToSymbol(c_cg_dense, dense.data(), dense.size() * sizeof(float)));
   }
   CK(cudaMemcpyToSymbol(c_atom14_group, cfg->atom14_group, sizeof(int) * 21 * 14));
   int rc;
@@ -498,6 +511,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
 void b200dock_destroy(B200Handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (g_plan_owner[h->device & 63] == h) g_plan_owner[h->device & 63] = nullptr;
   auto fr = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
   for (auto& w : h->cw) { fr(w.counts); fr(w.seg); fr(w.es); fr(w.ed); fr(w.eaux); fr(w.emb); fr(w.sh); fr(w.H1); fr(w.H1lo); fr(w.Zt); fr(w.msg); }
   for (auto& b : h->pre) fr(b);

@@ -10,6 +10,7 @@
 #define KP B200_K_PAD       // padded K of the weight generator
 #define TILE_E 128          // edges per prologue tile (= tcgen05 M)
 #define SIG 32              // sigma / distance embedding width
+#define B200_MAX_CHUNKS 96
 
 struct DevPlan {            // device mirror of B200ConvPlan (pointers are device pointers)
   int n_paths;
@@ -21,9 +22,10 @@ struct DevPlan {            // device mirror of B200ConvPlan (pointers are devic
   const int* cg_ijk;
   const float* cg_val;
   int n_chunks;
-  const int* chunk_col;
-  const int* chunk_n;
-  const int* chunk_path;
+  // chunk tables live in constant memory with the plan: they sit on the MMA issue path
+  int chunk_col[B200_MAX_CHUNKS];
+  int chunk_n[B200_MAX_CHUNKS];
+  int chunk_path[B200_MAX_CHUNKS];
 };
 
 // fp32 arithmetic without FMA contraction where bit-parity with the oracle matters

@@ -557,27 +557,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
             pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
           }
-          float mx = 1.0f;                               // the ones column
-#pragma unroll 4
-          for (int k4 = 0; k4 < 36; ++k4) {
-            float4 f;
-            if (k4 < 12) f = __ldg(pe + k4);
-            else if (k4 < 24) f = __ldg(pa + (k4 - 12));
-            else {
-              f = __ldg(pb0 + (k4 - 24));
-              if (pb1) { float4 f2 = __ldg(pb1 + (k4 - 24)); f.x += f2.x; f.y += f2.y; f.z += f2.z; f.w += f2.w; }
+          float4 xf[36];                                 // the whole edge-input row in flight at once
+#pragma unroll
+          for (int k4 = 0; k4 < 12; ++k4) xf[k4] = __ldg(pe + k4);
+#pragma unroll
+          for (int k4 = 0; k4 < 12; ++k4) xf[12 + k4] = __ldg(pa + k4);
+#pragma unroll
+          for (int k4 = 0; k4 < 12; ++k4) xf[24 + k4] = __ldg(pb0 + k4);
+          if (pb1) {
+#pragma unroll
+            for (int k4 = 0; k4 < 12; ++k4) {
+              float4 f2 = __ldg(pb1 + k4);
+              xf[24 + k4].x += f2.x; xf[24 + k4].y += f2.y; xf[24 + k4].z += f2.z; xf[24 + k4].w += f2.w;
             }
-            xrow[4 * k4] = f.x; xrow[4 * k4 + 1] = f.y; xrow[4 * k4 + 2] = f.z; xrow[4 * k4 + 3] = f.w;
-            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w))));
           }
+          float mx = 1.0f;                               // the ones column
+#pragma unroll
+          for (int k4 = 0; k4 < 36; ++k4)
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(xf[k4].x), fabsf(xf[k4].y)), fmaxf(fabsf(xf[k4].z), fabsf(xf[k4].w))));
           sx = tc::row_scale(mx);
-#pragma unroll 1
+#pragma unroll
           for (int g = 0; g < 3; ++g) {
             float v[64];
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const int k = g * 64 + j;
-              v[j] = (k < 144) ? xrow[k] * sx : (k == 144 ? sx : 0.0f);
+            for (int j = 0; j < 16; ++j) {
+              const int k4 = g * 16 + j;
+              float4 f = (k4 < 36) ? xf[k4 < 36 ? k4 : 0] : make_float4(k4 == 36 ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
+              v[4 * j] = f.x * sx; v[4 * j + 1] = f.y * sx; v[4 * j + 2] = f.z * sx; v[4 * j + 3] = f.w * sx;
             }
             tc::pack_store_f16(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(ACOLS + g * 32), v);
           }
@@ -588,10 +594,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         // ---- x1 row -> per-thread scratch, edge harmonics -> registers
         {
           const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
-          const int nq = (P.in_dim + 3) >> 2;
-          for (int qq = 0; qq < nq; ++qq) {
-            float4 f = __ldg(px + qq);
-            xrow[4 * qq] = f.x; xrow[4 * qq + 1] = f.y; xrow[4 * qq + 2] = f.z; xrow[4 * qq + 3] = f.w;
+          const int nq = (P.in_dim + 3) >> 2;            // 12, 21, 30 or 42 float4
+#pragma unroll 1
+          for (int q0 = 0; q0 < nq; q0 += 14) {
+            float4 f[14];
+#pragma unroll
+            for (int j = 0; j < 14; ++j) f[j] = (q0 + j < nq) ? __ldg(px + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 14; ++j)
+              if (q0 + j < nq) {
+                float* o = xrow + 4 * (q0 + j);
+                o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
+              }
           }
         }
         float shv[9];

@@ -99,9 +99,10 @@ def sinusoidal_embedding(t: torch.Tensor, dim: int = 32, scale: float = 1000.0) 
 class Engine:
     """One handle = one device.  ``conv_kernel``: 0 SIMT fp32 (exact), 1 tcgen05 3xTF32 (H1 in smem),
     2 tcgen05 single TF32 (fast, ~1e-3), 3 tcgen05 3xTF32 with H1 resident in tensor memory,
-    4 fully fused tcgen05 3xTF32 conv (both FC layers + fold in one kernel; default)."""
+    4 fully fused tcgen05 3xTF32 conv (both FC layers + fold in one kernel),
+    5 the fused kernel with FP16 hi/lo error-compensated MMAs and per-row scaling (default, fp32-grade)."""
 
-    def __init__(self, device: int = 0, conv_kernel: int = 4):
+    def __init__(self, device: int = 0, conv_kernel: int = 5):
         if not torch.cuda.is_available():
             raise RuntimeError("diffbindfr_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = load_library()

@@ -88,7 +88,8 @@ typedef struct {
 typedef struct {
   B200ConvPlan plans[B200_N_PLANS];
   int32_t conv_kernel;      /* 0 SIMT fp32, 1 tcgen05 3xTF32 (A in smem), 2 tcgen05 TF32, 3 tcgen05 3xTF32 (A in TMEM),
-                               4 fully fused tcgen05 3xTF32 conv (default) */
+                               4 fully fused tcgen05 3xTF32 conv,
+                               5 fused conv with FP16 hi/lo MMAs + per-row scaling (default) */
   int32_t reserved[7];
   const int32_t* atom14_group;  /* [21][14] restype_atom14_to_rigid_group (protein_constants.py:1177-1199) */
   /* sparse CG tables of the pseudo-torque product harmonics: triples (2,2,0), (1,2,1), (2,2,1) */

@@ -13,7 +13,7 @@ from helpers import conditioning, load_golden, rmsd
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,4").split(",") if k]
+KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,4,5").split(",") if k]
 # fp32 score tolerance: |cuda - oracle_fp32| <= RTOL * max|oracle| (fp32 oracle itself is ~2e-6 from fp64)
 RTOL = {0: 2e-4, 1: 2e-4, 2: 5e-2, 3: 2e-4, 4: 2e-4, 5: 2e-4}
 
@@ -165,7 +165,7 @@ def test_plugin_forward_and_sample_mirror_reference_interface(sd):
     from diffbindfr_b200 import plugin
     g = load_golden("score_tiny.pt")
     b = synth.make_batch(**g["workload"], seed=g["seed"])
-    model = plugin.TensorProductModel(None, conv_kernel=4)
+    model = plugin.TensorProductModel(None, conv_kernel=5)
     model.load_state_dict(sd, strict=True)
     data = _AttrDict({k: (v.clone() if torch.is_tensor(v) else v) for k, v in b.items()})
     data.update(conditioning(b, **g["cond"]))
@@ -186,3 +186,24 @@ def test_plugin_forward_and_sample_mirror_reference_interface(sd):
     assert len(out) == b["num_graphs"] and out[0][0].shape[0] == 20 and out[0][1].shape[2:] == (14, 3)
     lig = torch.cat([o[0][-1] for o in out]); a14 = torch.cat([o[1][-1] for o in out])
     assert rmsd(lig, gs["lig_traj"][-1]) <= 1e-3 and rmsd(a14, gs["atom14_final"]) <= 1e-3
+
+
+@pytest.mark.parametrize("w1_scale,w2_scale", [(40.0, 1e-3), (0.02, 30.0)])
+def test_fp16_mode_is_robust_to_weight_and_activation_scale(sd, w1_scale, w2_scale):
+    """Mode 5 splits operands into fp16 hi/lo with exact power-of-two scaling (per conv for W, per edge row
+    for activations): large / tiny hidden activations and weights must not cost accuracy."""
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    for k in sd2:
+        if ".fc.lin.0." in k:
+            sd2[k] = sd2[k] * w1_scale
+        if ".fc.lin.3." in k:
+            sd2[k] = sd2[k] * w2_scale
+    eng = make_engine(5, sd2)
+    b = synth.make_batch(**synth.WORKLOADS["tiny"], seed=6)
+    c = conditioning(b)
+    out = run_score(eng, b, c)
+    d = dict(b); d.update(c)
+    ref = omodel.score_model(sd2, d, torch.float64)
+    for k, o, r in zip(("tr", "rot", "tor", "sc"), out, ref):
+        assert torch.isfinite(o).all(), k
+        assert (o.double() - r).abs().max().item() <= 2e-4 * max(r.abs().max().item(), 1e-6), k

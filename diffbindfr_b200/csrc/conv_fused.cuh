@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused(ConvLaunch L, cons
             if (tc::elect_one()) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
+                if (ka == TC_KATOMS - 1 && k8 == 3) continue;   // columns 152..159 are zero padding
                 const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + KP;
                 tc::mma_tf32_ts(d_tmem, a_lo, dh + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
                 tc::mma_tf32_ts(d_tmem, a_hi, dl + (uint64_t)(k8 * 2), idesc, 1u);
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             if (tc::elect_one()) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
+                if (ka == KATOMS - 1 && k8 >= 2) continue;   // K = 145 real columns: halves 160..191 are zero padding
                 const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + ACOLS;
                 tc::mma_f16_ts(d_tmem, a_lo, dhs[ka] + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
                 tc::mma_f16_ts(d_tmem, a_hi, dls[ka] + (uint64_t)(k8 * 2), idesc, 1u);

@@ -169,9 +169,9 @@ EdgeMlp edge_mlp(const B200Handle* h, int section, int n_bond, int n_sigma) {
 template <int KIND>
 int build_graph(B200Handle* h, const GraphArgs& G, ConvWs& w, cudaStream_t st) {
   if (w.T == 0) return B200_OK;
-  k_graph_count<KIND><<<grid_for(w.T, 128, 148 * 8), 128, 0, st>>>(G, w.T, w.counts.as<int>());
+  k_graph_count<KIND><<<grid_for((long long)w.T * 32, 256, 148 * 8), 256, 0, st>>>(G, w.T, w.counts.as<int>());
   k_scan<<<1, 1024, 0, st>>>(w.counts.as<int>(), w.T, w.seg.as<int>());
-  k_graph_fill<KIND><<<grid_for(w.T, 128, 148 * 8), 128, 0, st>>>(G, w.T, w.seg.as<int>(), w.cap - 128, w.es.as<int>(),
+  k_graph_fill<KIND><<<grid_for((long long)w.T * 32, 256, 148 * 8), 256, 0, st>>>(G, w.T, w.seg.as<int>(), w.cap - 128, w.es.as<int>(),
                                                                w.ed.as<int>(), KIND == G_LIG ? w.eaux.as<int>() : nullptr,
                                                                h->errflag.as<int>());
   h->launches += 3;
@@ -322,11 +322,11 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     U.N = b.N_l; U.h = hl;
     U.seg[0] = h->cw[0].seg.as<int>(); U.msg[0] = h->cw[0].msg.as<float>(); U.ln[0] = h->convw[0 * 6 + l].ln;
     U.seg[1] = h->cw[2].seg.as<int>(); U.msg[1] = h->cw[2].msg.as<float>(); U.ln[1] = h->convw[2 * 6 + l].ln;
-    k_node_update<<<grid_for(b.N_l, 8, 148 * 8), 256, 0, st>>>(U);
+    k_node_update<4><<<grid_for(b.N_l, 2, 148 * 16), 256, 0, st>>>(U);   // long segments: 4 warps per ligand atom
     U.N = b.N_a; U.h = ha;
     U.seg[0] = h->cw[1].seg.as<int>(); U.msg[0] = h->cw[1].msg.as<float>(); U.ln[0] = h->convw[1 * 6 + l].ln;
     U.seg[1] = h->cw[3].seg.as<int>(); U.msg[1] = h->cw[3].msg.as<float>(); U.ln[1] = h->convw[3 * 6 + l].ln;
-    k_node_update<<<grid_for(b.N_a, 8, 148 * 8), 256, 0, st>>>(U);
+    k_node_update<1><<<grid_for(b.N_a, 8, 148 * 8), 256, 0, st>>>(U);
     h->launches += 2;
   }
   // ---- translation / rotation heads

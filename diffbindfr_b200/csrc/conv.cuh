@@ -328,41 +328,57 @@ struct NodeUpdateArgs {
   int plan;
 };
 
-// mean over the segment + LayerNorm of one source; result left in row[] (shared, per warp)
-__device__ __forceinline__ void segment_mean_ln(const DevPlan& P, const int* seg, const float* msg, LnParams ln,
-                                                int n, float* row, int lane) {
+// Segment sum of one source by WPN cooperating warps (warp w takes edges p0+w, p0+w+WPN, ...), 4 rows in
+// flight per lane; the partial sums meet in shared memory, then the node's first warp applies the mean and the
+// equivariant LayerNorm.  Result left in the first partial row (shared).
+template <int WPN>
+__device__ __forceinline__ void segment_partial(const DevPlan& P, const int* seg, const float* msg, int n, int w,
+                                                float* part /* [WPN][HS] */, int lane) {
   const int p0 = seg[n], p1 = seg[n + 1];
-  const float cnt = (float)max(p1 - p0, 1);
-  const int nc = (P.out_dim + 31) / 32;
   float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int e = p0;
-  for (; e + 4 <= p1; e += 4) {                       // 4 rows in flight per lane
+  int e = p0 + w;
+  for (; e + 3 * WPN < p1; e += 4 * WPN) {
     float v[4][6];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
         int c = lane + 32 * q;
-        v[r][q] = (q < nc && c < P.out_dim) ? msg[(size_t)(e + r) * HS + c] : 0.0f;
+        v[r][q] = (c < P.out_dim) ? msg[(size_t)(e + r * WPN) * HS + c] : 0.0f;
       }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
       for (int q = 0; q < 6; ++q) s[q] += v[r][q];
   }
-  for (; e < p1; ++e)
+  for (; e < p1; e += WPN)
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       int c = lane + 32 * q;
-      if (q < nc && c < P.out_dim) s[q] += msg[(size_t)e * HS + c];
+      if (c < P.out_dim) s[q] += msg[(size_t)e * HS + c];
     }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
     int c = lane + 32 * q;
-    if (c < P.out_dim) row[c] = s[q] / cnt;
+    if (c < P.out_dim) part[w * HS + c] = s[q];
+  }
+}
+
+template <int WPN>
+__device__ __forceinline__ void mean_ln(const DevPlan& P, const int* seg, LnParams ln, int n, float* part, int lane) {
+  float* row = part;                                   // result overwrites the first partial row
+  const float cnt = (float)max(seg[n + 1] - seg[n], 1);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    int c = lane + 32 * q;
+    if (c < P.out_dim) {
+      float s = part[c];
+#pragma unroll
+      for (int w = 1; w < WPN; ++w) s += part[w * HS + c];
+      row[c] = s / cnt;
+    }
   }
   __syncwarp();
-  // per-block statistics, lanes split the multiplicity
   float fm[B200_MAX_BLOCKS][3], scl[B200_MAX_BLOCKS];
   for (int b = 0; b < P.n_blocks; ++b) {
     const B200Block bl = P.blocks[b];
@@ -410,21 +426,50 @@ __device__ __forceinline__ void segment_mean_ln(const DevPlan& P, const int* seg
   __syncwarp();
 }
 
+// single-warp convenience wrapper (pseudo-torque read-outs)
+__device__ __forceinline__ void segment_mean_ln(const DevPlan& P, const int* seg, const float* msg, LnParams ln,
+                                                int n, float* row, int lane) {
+  segment_partial<1>(P, seg, msg, n, 0, row, lane);
+  __syncwarp();
+  mean_ln<1>(P, seg, ln, n, row, lane);
+}
+
+// h[n] += LN_0(mean_0) + LN_1(mean_1)  (tpscore.py:513-516); WPN warps cooperate on one node
+template <int WPN>
 __global__ void __launch_bounds__(256) k_node_update(NodeUpdateArgs A) {
-  __shared__ float rows[8][HS];
+  constexpr int NPB = 8 / WPN;                         // nodes per block
+  __shared__ float parts[8][HS];
   const DevPlan& P = c_plans[A.plan];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  for (int n = blockIdx.x * 8 + wib; n < A.N; n += gridDim.x * 8) {
+  const int slot = wib / WPN, w = wib % WPN;
+  for (int base = blockIdx.x * NPB; base < A.N; base += gridDim.x * NPB) {
+    const int n = base + slot;
+    const bool valid = n < A.N;
     float acc[6];
-    int ri = 0;
-    for (int c = lane; c < P.out_dim; c += 32, ++ri) acc[ri] = A.h[(size_t)n * HS + c];
-    for (int s = 0; s < 2; ++s) {
-      segment_mean_ln(P, A.seg[s], A.msg[s], A.ln[s], n, rows[wib], lane);
-      ri = 0;
-      for (int c = lane; c < P.out_dim; c += 32, ++ri) acc[ri] += rows[wib][c];
-      __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      int c = lane + 32 * q;
+      acc[q] = (valid && w == 0 && c < P.out_dim) ? A.h[(size_t)n * HS + c] : 0.0f;
     }
-    ri = 0;
-    for (int c = lane; c < P.out_dim; c += 32, ++ri) A.h[(size_t)n * HS + c] = acc[ri];
+    for (int s = 0; s < 2; ++s) {
+      if (valid) segment_partial<WPN>(P, A.seg[s], A.msg[s], n, w, parts[slot * WPN], lane);
+      if (WPN > 1) __syncthreads(); else __syncwarp();
+      if (valid && w == 0) {
+        mean_ln<WPN>(P, A.seg[s], A.ln[s], n, parts[slot * WPN], lane);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          int c = lane + 32 * q;
+          if (c < P.out_dim) acc[q] += parts[slot * WPN][c];
+        }
+      }
+      if (WPN > 1) __syncthreads(); else __syncwarp();
+    }
+    if (valid && w == 0) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        int c = lane + 32 * q;
+        if (c < P.out_dim) A.h[(size_t)n * HS + c] = acc[q];
+      }
+    }
   }
 }

@@ -48,78 +48,89 @@ __device__ __forceinline__ bool is_cab(const int* pocket_feat, int a) {
   return id == 1 || id == 3;  // atom_order['CA'], atom_order['CB'] (protein_constants.py:561-600)
 }
 
-// Enumerate the incoming edges of `target` in a fixed order; f(d, aux) is called per edge where
-// d is the gather-side endpoint (edge_index[1]) and aux the bond id (ligand graph) or -1.
-template <int KIND, typename F>
-__device__ __forceinline__ void for_each_edge(const GraphArgs& A, int target, F f) {
-  if (KIND == G_LIG) {
-    int s = target;
-    for (int b = A.bond_ptr[s]; b < A.bond_ptr[s + 1]; ++b) f(A.bond_dst[b], A.bond_eid[b]);
-    int g = A.lig_batch[s];
-    float x = A.lig_pos[3 * s], y = A.lig_pos[3 * s + 1], z = A.lig_pos[3 * s + 2];
-    for (int i = A.lig_ptr[g]; i < A.lig_ptr[g + 1]; ++i) {
-      if (i == s) continue;
-      float d2 = dist2_nofma(x, y, z, A.lig_pos[3 * i], A.lig_pos[3 * i + 1], A.lig_pos[3 * i + 2]);
-      if (d2 < 25.0f && s <= A.lig_jmax[i]) f(i, -1);
-    }
-  } else if (KIND == G_ATOM) {
-    int s = target;
-    int g = A.atom_batch[s];
-    float x = A.atom_pos[3 * s], y = A.atom_pos[3 * s + 1], z = A.atom_pos[3 * s + 2];
-    for (int i = A.atom_ptr[g]; i < A.atom_ptr[g + 1]; ++i) {
-      if (i == s) continue;
-      float d2 = dist2_nofma(x, y, z, A.atom_pos[3 * i], A.atom_pos[3 * i + 1], A.atom_pos[3 * i + 2]);
-      if (d2 < 16.0f && s <= A.atom_jmax[i]) f(i, -1);
-    }
-  } else if (KIND == G_AL) {   // target = ligand atom l, d = pocket atom a
-    int l = target;
-    int g = A.lig_batch[l];
-    float c = __fadd_rn(__fmul_rn(A.tr_sigma[g], 0.2f), 5.0f);   // tpscore.py:654
-    float x = A.lig_pos[3 * l] / c, y = A.lig_pos[3 * l + 1] / c, z = A.lig_pos[3 * l + 2] / c;
-    for (int a = A.atom_ptr[g]; a < A.atom_ptr[g + 1]; ++a) {
-      if (is_cab(A.pocket_feat, a)) { f(a, -1); continue; }
-      float d2 = dist2_nofma(A.atom_pos[3 * a] / c, A.atom_pos[3 * a + 1] / c, A.atom_pos[3 * a + 2] / c, x, y, z);
-      if (d2 < 1.0f) f(a, -1);
-    }
-  } else if (KIND == G_LA) {   // target = pocket atom a, d = ligand atom l
-    int a = target;
-    int g = A.atom_batch[a];
-    float c = __fadd_rn(__fmul_rn(A.tr_sigma[g], 0.2f), 5.0f);
-    bool cab = is_cab(A.pocket_feat, a);
-    float x = A.atom_pos[3 * a] / c, y = A.atom_pos[3 * a + 1] / c, z = A.atom_pos[3 * a + 2] / c;
-    for (int l = A.lig_ptr[g]; l < A.lig_ptr[g + 1]; ++l) {
-      if (cab) { f(l, -1); continue; }
-      float d2 = dist2_nofma(x, y, z, A.lig_pos[3 * l] / c, A.lig_pos[3 * l + 1] / c, A.lig_pos[3 * l + 2] / c);
-      if (d2 < 1.0f) f(l, -1);
-    }
-  } else {                     // G_TOR / G_SC: target = bond, d = atom within r of the bond midpoint, cap 32
-    const float* pos = (KIND == G_TOR) ? A.lig_pos : A.atom_pos;
-    const int* batch = (KIND == G_TOR) ? A.lig_batch : A.atom_batch;
-    const int* ptr = (KIND == G_TOR) ? A.lig_ptr : A.atom_ptr;
-    const int* bonds = (KIND == G_TOR) ? A.tor_bonds : A.sc_bonds;
-    const float r2 = (KIND == G_TOR) ? 25.0f : 16.0f;
-    int b0 = bonds[2 * target], b1 = bonds[2 * target + 1];
-    float mx = __fadd_rn(pos[3 * b0], pos[3 * b1]) / 2.0f;
-    float my = __fadd_rn(pos[3 * b0 + 1], pos[3 * b1 + 1]) / 2.0f;
-    float mz = __fadd_rn(pos[3 * b0 + 2], pos[3 * b1 + 2]) / 2.0f;
-    int g = batch[b0];
-    int cnt = 0;
-    for (int a = ptr[g]; a < ptr[g + 1]; ++a) {
-      float d2 = dist2_nofma(pos[3 * a], pos[3 * a + 1], pos[3 * a + 2], mx, my, mz);
-      if (d2 < r2) {
-        f(a, -1);
-        if (++cnt == 32) break;
-      }
-    }
-  }
+// Candidate range and membership predicate of one (target, candidate) pair; candidates are walked in
+// ascending index so every segment is emitted in ascending candidate order (ligand bonds first).
+template <int KIND>
+__device__ __forceinline__ void cand_range(const GraphArgs& A, int t, int& lo, int& hi) {
+  int g;
+  if (KIND == G_LIG || KIND == G_AL) g = A.lig_batch[t];
+  else if (KIND == G_ATOM || KIND == G_LA) g = A.atom_batch[t];
+  else if (KIND == G_TOR) g = A.lig_batch[A.tor_bonds[2 * t]];
+  else g = A.atom_batch[A.sc_bonds[2 * t]];
+  const int* ptr = (KIND == G_LIG || KIND == G_LA || KIND == G_TOR) ? A.lig_ptr : A.atom_ptr;
+  lo = ptr[g]; hi = ptr[g + 1];
 }
 
 template <int KIND>
-__global__ void k_graph_count(GraphArgs A, int T, int* __restrict__ counts) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-    int c = 0;
-    for_each_edge<KIND>(A, t, [&](int, int) { ++c; });
-    counts[t] = c;
+struct TargetCtx { float x, y, z, c; bool cab; };
+
+template <int KIND>
+__device__ __forceinline__ TargetCtx<KIND> target_ctx(const GraphArgs& A, int t) {
+  TargetCtx<KIND> T{};
+  if (KIND == G_LIG) { T.x = A.lig_pos[3 * t]; T.y = A.lig_pos[3 * t + 1]; T.z = A.lig_pos[3 * t + 2]; }
+  else if (KIND == G_ATOM) { T.x = A.atom_pos[3 * t]; T.y = A.atom_pos[3 * t + 1]; T.z = A.atom_pos[3 * t + 2]; }
+  else if (KIND == G_AL) {
+    T.c = __fadd_rn(__fmul_rn(A.tr_sigma[A.lig_batch[t]], 0.2f), 5.0f);
+    T.x = A.lig_pos[3 * t] / T.c; T.y = A.lig_pos[3 * t + 1] / T.c; T.z = A.lig_pos[3 * t + 2] / T.c;
+  } else if (KIND == G_LA) {
+    T.c = __fadd_rn(__fmul_rn(A.tr_sigma[A.atom_batch[t]], 0.2f), 5.0f);
+    T.cab = is_cab(A.pocket_feat, t);
+    T.x = A.atom_pos[3 * t] / T.c; T.y = A.atom_pos[3 * t + 1] / T.c; T.z = A.atom_pos[3 * t + 2] / T.c;
+  } else {
+    const float* pos = (KIND == G_TOR) ? A.lig_pos : A.atom_pos;
+    const int* bonds = (KIND == G_TOR) ? A.tor_bonds : A.sc_bonds;
+    int b0 = bonds[2 * t], b1 = bonds[2 * t + 1];
+    T.x = __fadd_rn(pos[3 * b0], pos[3 * b1]) / 2.0f;
+    T.y = __fadd_rn(pos[3 * b0 + 1], pos[3 * b1 + 1]) / 2.0f;
+    T.z = __fadd_rn(pos[3 * b0 + 2], pos[3 * b1 + 2]) / 2.0f;
+  }
+  return T;
+}
+
+template <int KIND>
+__device__ __forceinline__ bool edge_pred(const GraphArgs& A, const TargetCtx<KIND>& T, int t, int i) {
+  if (KIND == G_LIG) {
+    if (i == t) return false;
+    float d2 = dist2_nofma(T.x, T.y, T.z, A.lig_pos[3 * i], A.lig_pos[3 * i + 1], A.lig_pos[3 * i + 2]);
+    return d2 < 25.0f && t <= A.lig_jmax[i];
+  } else if (KIND == G_ATOM) {
+    if (i == t) return false;
+    float d2 = dist2_nofma(T.x, T.y, T.z, A.atom_pos[3 * i], A.atom_pos[3 * i + 1], A.atom_pos[3 * i + 2]);
+    return d2 < 16.0f && t <= A.atom_jmax[i];
+  } else if (KIND == G_AL) {
+    if (is_cab(A.pocket_feat, i)) return true;
+    float d2 = dist2_nofma(A.atom_pos[3 * i] / T.c, A.atom_pos[3 * i + 1] / T.c, A.atom_pos[3 * i + 2] / T.c, T.x, T.y, T.z);
+    return d2 < 1.0f;
+  } else if (KIND == G_LA) {
+    if (T.cab) return true;
+    float d2 = dist2_nofma(T.x, T.y, T.z, A.lig_pos[3 * i] / T.c, A.lig_pos[3 * i + 1] / T.c, A.lig_pos[3 * i + 2] / T.c);
+    return d2 < 1.0f;
+  } else {
+    const float* pos = (KIND == G_TOR) ? A.lig_pos : A.atom_pos;
+    const float r2 = (KIND == G_TOR) ? 25.0f : 16.0f;
+    return dist2_nofma(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], T.x, T.y, T.z) < r2;
+  }
+}
+
+// One warp per target: lanes test 32 candidates at a time, ballots keep the ascending-index order.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_graph_count(GraphArgs A, int T, int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < T; t += warps) {
+    int lo, hi;
+    cand_range<KIND>(A, t, lo, hi);
+    const TargetCtx<KIND> C = target_ctx<KIND>(A, t);
+    int c = (KIND == G_LIG) ? (A.bond_ptr[t + 1] - A.bond_ptr[t]) : 0;
+    int kept = 0;
+    for (int i0 = lo; i0 < hi; i0 += 32) {
+      const int i = i0 + lane;
+      const bool p = (i < hi) && edge_pred<KIND>(A, C, t, i);
+      int n = __popc(__ballot_sync(0xffffffffu, p));
+      if (KIND == G_TOR || KIND == G_SC) { n = min(n, 32 - kept); kept += n; }
+      c += n;
+    }
+    if (lane == 0) counts[t] = c;
   }
 }
 
@@ -145,20 +156,40 @@ __global__ void k_scan(const int* __restrict__ counts, int T, int* __restrict__ 
 }
 
 template <int KIND>
-__global__ void k_graph_fill(GraphArgs A, int T, const int* __restrict__ seg_ptr, int cap, int* __restrict__ es,
-                             int* __restrict__ ed, int* __restrict__ eaux, int* __restrict__ err_flag) {
+__global__ void __launch_bounds__(256) k_graph_fill(GraphArgs A, int T, const int* __restrict__ seg_ptr, int cap,
+                                                    int* __restrict__ es, int* __restrict__ ed, int* __restrict__ eaux,
+                                                    int* __restrict__ err_flag) {
   int total = seg_ptr[T];
   if (total > cap) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(err_flag, 1 + KIND);
     return;
   }
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < T; t += warps) {
     int p = seg_ptr[t];
-    for_each_edge<KIND>(A, t, [&](int d, int aux) {
-      es[p] = t; ed[p] = d;
-      if (eaux) eaux[p] = aux;
-      ++p;
-    });
+    if (KIND == G_LIG) {
+      const int b0 = A.bond_ptr[t], nb = A.bond_ptr[t + 1] - b0;
+      for (int b = lane; b < nb; b += 32) { es[p + b] = t; ed[p + b] = A.bond_dst[b0 + b]; eaux[p + b] = A.bond_eid[b0 + b]; }
+      p += nb;
+    }
+    int lo, hi;
+    cand_range<KIND>(A, t, lo, hi);
+    const TargetCtx<KIND> C = target_ctx<KIND>(A, t);
+    int kept = 0;
+    for (int i0 = lo; i0 < hi; i0 += 32) {
+      const int i = i0 + lane;
+      bool pr = (i < hi) && edge_pred<KIND>(A, C, t, i);
+      const unsigned m = __ballot_sync(0xffffffffu, pr);
+      const int rank = __popc(m & ((1u << lane) - 1u));
+      int n = __popc(m);
+      if (KIND == G_TOR || KIND == G_SC) { pr = pr && (kept + rank < 32); n = min(n, 32 - kept); kept += n; }
+      if (pr) {
+        es[p + rank] = t; ed[p + rank] = i;
+        if (eaux) eaux[p + rank] = -1;
+      }
+      p += n;
+    }
   }
   // pad the tail of the last 128-edge tile with a harmless self edge
   int padded = min(((total + TILE_E - 1) / TILE_E) * TILE_E, cap);

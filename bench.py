@@ -256,11 +256,22 @@ def main():
     # last step's edge counts stand in for all K steps (they drift by <1 % as poses move)
     f_tp = tp_flops(counts)
     achieved = f_tp * K / (tp_ms * 1e-3) / 1e12 if tp_ms > 0 else None
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_extract.py)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fused16_ncu_step.json")))
+        if args.conv_kernel == 5 and args.workload == "cfgA":
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     kname = {0: "k_conv_tp_simt (fp32 SIMT)", 1: "k_conv_tp_tc<1> (tcgen05 3xTF32, H1 in smem)", 2: "k_conv_tp_tc<2> (tcgen05 TF32)", 3: "k_conv_tp_tc3 (tcgen05 3xTF32, H1 in TMEM)", 4: "k_conv_fused (tcgen05 3xTF32, both FC layers + fold fused)", 5: "k_conv_fused16 (tcgen05 3xFP16 split, fused)"}[args.conv_kernel]
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+            "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
             "kernel": kname, "kernel_ms_per_step": tp_ms / K, "kernel_share_of_step": tp_ms / ms_total,
-            "launches_per_step": tp_launches / K, "algorithmic_flops_per_step": f_tp, "peak_source": peak_src}
+            "launches_per_step": tp_launches / K, "algorithmic_flops_per_step": f_tp, "peak_source": peak_src,
+            "algorithmic_flops_per_launch": f_tp * K / max(tp_launches, 1),
+            "note": "achieved = algorithmic FLOPs of all tensor-product launches of the timed region / their summed CUDA-event time; "
+                    "the kernel issues 3 fp16 MMAs per algorithmic MAC (hi/lo error compensation), so the tensor pipe does ~3x this; "
+                    "traffic = mean DRAM bytes per launch over one step (8 launches) from the committed ncu capture"}
     cpu = None
     if not args.no_cpu_baseline:
         cpu = cpu_baseline(n_poses=args.cpu_baseline_poses, steps=1)
@@ -268,7 +279,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 4: "tf32x3", 5: "fp16x3"}[args.conv_kernel], "data": "synthetic",
             "config": {"workload": f"{args.workload}: 1 complex x 40 poses x 36 residues (~300 pocket atoms) x 30 ligand atoms per GPU"
-                       if args.workload == "cfgA" else args.workload,
+                       if args.workload == "cfgA" else f"{args.workload}: {workload_kwargs(args.workload)} per GPU",
                        "poses_per_gpu": int(b["num_graphs"]), "pocket_atoms": int(b["rec_atm_pos"].shape[0]),
                        "ligand_atoms": int(b["lig_pos"].shape[0]), "edges": counts, "conv_kernel": args.conv_kernel,
                        "random_init_weights": True, "parallelism": f"pose-sharded x{world}, one final all_gather",

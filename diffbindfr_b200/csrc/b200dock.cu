@@ -15,6 +15,7 @@
 #include "conv_fused.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
+#include "mdn.cuh"
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -61,6 +62,7 @@ struct B200Handle {
   ConvWs cw[6];
   Buf pre[6], h_lig, h_atom, jmax_lig, jmax_atom, centre, cmsg, s_tr, s_rot, s_tor, s_sc, atom14, errflag;
   Buf c_temb, c_trs, c_rotn, c_torn, c_scn, temb_steps;
+  Buf mdn_w, mdn_A, mdn_B; bool mdn_weights = false;
   // host-batch path
   Buf pinned_in, dev_in, dev_noise, dev_lig_out, dev_a14_out, pinned_out;
   int64_t launches = 0;
@@ -73,6 +75,7 @@ struct B200Handle {
   int debug_layers = 6;
   int tp_grid = 148;
   std::vector<float> cg_dense;
+  int dbg_flag = 0;
 };
 
 namespace {
@@ -310,7 +313,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     const int plan = plan_of_layer(l);
     ConvLaunch L{};
     TcExtra X{};
-    L.n = 4;
+    L.n = 4; L.dbg = h->dbg_flag;
     L.c[0] = conv_args(h, h->cw[0], 0 * 6 + l, plan, hl, hl, 0, nullptr, 9, X, 0);     // lig
     L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9, X, 1);     // atom
     L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9, X, 2);     // al: target lig, gather atom
@@ -459,6 +462,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   h->n_sms = prop.multiProcessorCount;
   h->tp_grid = h->n_sms;
+  if (const char* g = getenv("B200DOCK_DBG")) h->dbg_flag = atoi(g);
   if (const char* g = getenv("B200DOCK_TP_GRID")) { int v = atoi(g); if (v > 0 && v <= h->n_sms) h->tp_grid = v; }
   for (int p = 0; p < B200_N_PLANS; ++p) {
     const B200ConvPlan& s = cfg->plans[p];
@@ -517,7 +521,7 @@ void b200dock_destroy(B200Handle* h) {
   for (auto& b : h->pre) fr(b);
   Buf* all[] = {&h->h_lig, &h->h_atom, &h->jmax_lig, &h->jmax_atom, &h->centre, &h->cmsg, &h->s_tr, &h->s_rot, &h->s_tor,
                 &h->s_sc, &h->atom14, &h->errflag, &h->c_temb, &h->c_trs, &h->c_rotn, &h->c_torn, &h->c_scn,
-                &h->temb_steps, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
+                &h->temb_steps, &h->mdn_w, &h->mdn_A, &h->mdn_B, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
   for (Buf* b : all) fr(*b);
   if (h->pinned_in.p) cudaFreeHost(h->pinned_in.p);
   if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
@@ -714,6 +718,38 @@ int b200dock_sample_host(B200Handle* h, const B200Batch* hb, const B200Step* ste
   memcpy(atom14_out, po + (size_t)b.N_l * 12, (size_t)b.N_r * 42 * 4);
   if (h2d_bytes) *h2d_bytes = total + (uint64_t)n_steps * SIG * 4;
   if (d2h_bytes) *d2h_bytes = out_bytes + 4;
+  return B200_OK;
+}
+
+int b200dock_mdn_load_weights(B200Handle* h, const float* blob, size_t n) {
+  if (!h || !blob) return B200_ERR_INVALID;
+  const size_t want = (size_t)MDN_H * MDN_H * 2 + MDN_H + (size_t)MDN_H * 30 + 30;
+  if (n != want) FAIL(B200_ERR_INVALID, "unexpected MDN weight blob size");
+  CK(cudaSetDevice(h->device));
+  ENS(h->mdn_w, n * sizeof(float));
+  CK(cudaMemcpy(h->mdn_w.p, blob, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->mdn_weights = true;
+  return B200_OK;
+}
+
+int b200dock_mdn_score(B200Handle* h, const B200MdnBatch* mb, float dist_threshold, float* score, void* stream) {
+  if (!h || !mb || !score) return B200_ERR_INVALID;
+  if (!h->mdn_weights) FAIL(B200_ERR_STATE, "MDN weights not loaded");
+  if (mb->B <= 0 || mb->N_l <= 0 || mb->N_r <= 0) FAIL(B200_ERR_INVALID, "empty MDN batch");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  ENS(h->mdn_A, (size_t)mb->N_l * MDN_H * 4); ENS(h->mdn_B, (size_t)mb->N_r * MDN_H * 4);
+  const float* W = h->mdn_w.as<float>();
+  const float* Wl = W; const float* Wr = W + MDN_H * MDN_H; const float* bias = Wr + MDN_H * MDN_H;
+  const float* W30 = bias + MDN_H; const float* b30 = W30 + MDN_H * 30;
+  k_mdn_project<<<grid_for(mb->N_l, 1, 148 * 8), MDN_H, 0, st>>>(mb->lig_s, mb->N_l, Wl, nullptr, h->mdn_A.as<float>());
+  k_mdn_project<<<grid_for(mb->N_r, 1, 148 * 8), MDN_H, 0, st>>>(mb->pro_s, mb->N_r, Wr, bias, h->mdn_B.as<float>());
+  MdnArgs M{};
+  M.B = mb->B; M.A = h->mdn_A.as<float>(); M.Bm = h->mdn_B.as<float>(); M.lig_pos = mb->lig_pos; M.lig_ptr = mb->lig_ptr;
+  M.xyz_full = mb->xyz_full; M.res_ptr = mb->res_ptr; M.W30t = W30; M.b30 = b30; M.thr = dist_threshold; M.score = score;
+  k_mdn_pairs<<<grid_for(mb->B, 1, 148 * 4), 256, 0, st>>>(M);
+  h->launches += 3;
+  CK(cudaGetLastError());
   return B200_OK;
 }
 

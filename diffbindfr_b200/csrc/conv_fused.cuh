@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
 #pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
             tc::mbar_wait(&b_full[ka], bpar);
-            tc::fence_after();
+            if (!(L.dbg & 8)) tc::fence_after();
             if (tc::elect_one()) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
@@ -559,6 +559,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
             pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
           }
+          if (!(L.dbg & 1)) {
           float4 xf[36];                                 // the whole edge-input row in flight at once
 #pragma unroll
           for (int k4 = 0; k4 < 12; ++k4) xf[k4] = __ldg(pe + k4);
@@ -589,6 +590,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             }
             tc::pack_store_f16(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(ACOLS + g * 32), v);
           }
+          }
           tc::tmem_wait_st();
           tc::fence_before();
           tc::mbar_arrive(x_full);
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
           const int nq = (P.in_dim + 3) >> 2;            // 12, 21, 30 or 42 float4
 #pragma unroll 1
-          for (int q0 = 0; q0 < nq; q0 += 14) {
+          for (int q0 = (L.dbg & 4) ? nq : 0; q0 < nq; q0 += 14) {
             float4 f[14];
 #pragma unroll
             for (int j = 0; j < 14; ++j) f[j] = (q0 + j < nq) ? __ldg(px + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
           float mx = 1.0f;
 #pragma unroll 1
-          for (int g = 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
+          for (int g = (L.dbg & 2) ? 9 : 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
             float v[16];
             tc::tmem_ld16(t0 + g * 16, v);
             tc::tmem_wait_ld();
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           shh = tc::row_scale(mx);
           const float sc1 = inv1 * shh;
 #pragma unroll 1
-          for (int g = 0; g < 3; ++g) {                  // pass 2: relu, scale, fp16 hi/lo, store
+          for (int g = (L.dbg & 2) ? 3 : 0; g < 3; ++g) {                  // pass 2: relu, scale, fp16 hi/lo, store
             float v[64];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {

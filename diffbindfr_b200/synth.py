@@ -281,4 +281,22 @@ WORKLOADS = {
     "3dbs": dict(n_complex=1, n_poses=1, n_res=105, n_lig=35),
     "3dbs_x40": dict(n_complex=1, n_poses=40, n_res=105, n_lig=35),
     "tiny": dict(n_complex=2, n_poses=2, n_res=10, n_lig=12),
+    # BASELINE.json configs[2..4] (single-GPU shards of the multi-GPU ones)
+    "cfg3_16x40": dict(n_complex=16, n_poses=40, n_res=36, n_lig=30),
+    "posebusters_32x40": dict(n_complex=32, n_poses=40, n_res=(30, 110), n_lig=(15, 50)),
+    "revdock_64x40": dict(n_complex=64, n_poses=40, n_res=36, n_lig=30),
 }
+
+
+def make_mdn_inputs(seed: int = 0, n_lig=(12, 30, 7), n_res=(20, 36, 11), missing: float = 0.3) -> Dict[str, torch.Tensor]:
+    """Seeded inputs of the MDN scoring head: encoder embeddings, ligand positions and
+    atom14 residue coordinates with missing atoms set to 0 like the reference featuriser."""
+    g = torch.Generator().manual_seed(seed)
+    nl, nr = list(n_lig), list(n_res)
+    B = len(nl)
+    xyz = torch.randn(sum(nr), 14, 3, generator=g) * 6
+    xyz[torch.rand(sum(nr), 14, generator=g) < missing] = 0.0
+    return dict(lig_s=torch.randn(sum(nl), 128, generator=g), pro_s=torch.randn(sum(nr), 128, generator=g),
+                lig_pos=torch.randn(sum(nl), 3, generator=g) * 4, xyz_full=xyz,
+                lig_batch=torch.repeat_interleave(torch.arange(B), torch.tensor(nl)),
+                pro_batch=torch.repeat_interleave(torch.arange(B), torch.tensor(nr)))

@@ -49,3 +49,16 @@ def random_state_dict(seed: int = 0, ln_jitter: float = 0.1, prefix: str = "") -
         off = torch.linspace(0.0, spec.GAUSSIAN_STOPS[base], spec.DIST_EMB)
         sd[prefix + name] = off if name.endswith("offset") else (-0.5 / (off[1] - off[0]) ** 2)
     return sd
+
+
+def random_mdn_state_dict(seed: int = 0, prefix: str = "mdn_layer.") -> Dict[str, torch.Tensor]:
+    """Seeded weights of the MDN scoring head with the reference's keys (MDN_Block.py:8-18)."""
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s, fan: (torch.rand(*s, generator=g) * 2 - 1) / math.sqrt(fan)
+    sd = {"MLP.0.weight": u(128, 256, fan=256), "MLP.0.bias": u(128, fan=256),
+          "MLP.1.weight": 1.0 + 0.2 * torch.randn(128, generator=g), "MLP.1.bias": 0.2 * torch.randn(128, generator=g),
+          "MLP.1.running_mean": 0.3 * torch.randn(128, generator=g), "MLP.1.running_var": 0.5 + 1.5 * torch.rand(128, generator=g),
+          "MLP.1.num_batches_tracked": torch.tensor(0)}
+    for h in ("z_pi", "z_sigma", "z_mu"):
+        sd[f"{h}.weight"] = u(10, 128, fan=128); sd[f"{h}.bias"] = u(10, fan=128)
+    return {prefix + k: v for k, v in sd.items()}

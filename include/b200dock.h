@@ -209,6 +209,24 @@ int b200dock_sample_host(B200Handle* h, const B200Batch* host_batch, const B200S
                          const float* time_emb, const float* noise, float* lig_out, float* atom14_out,
                          uint64_t* h2d_bytes, uint64_t* d2h_bytes, void* stream);
 
+/* MDN scoring head: KarmaDock.scoring(lig_s, lig_pos, pro_s, data, dist_threhold, batch_size)
+ * (DiffBindFR/scoring/architecture/KarmaDock_sc.py:87-101, MDN_Block.py:20-79; called from
+ * DiffBindFR/common/engines.py:285-294).  The encoders producing lig_s / pro_s are not part of the library yet. */
+typedef struct {
+  int32_t B, N_l, N_r;
+  const float* lig_s;             /* [N_l][128] ligand atom embeddings */
+  const float* lig_pos;           /* [N_l][3] */
+  const int32_t* lig_ptr;         /* [B+1] */
+  const float* pro_s;             /* [N_r][128] residue embeddings */
+  const float* xyz_full;          /* [N_r][14][3] atom14 coordinates (missing atoms = 0, as in the reference) */
+  const int32_t* res_ptr;         /* [B+1] */
+} B200MdnBatch;
+/* blob (host, 128*128*2 + 128 + 128*30 + 30 floats): Wl_t[128][128] Wr_t[128][128] bias[128] (Linear(256->128) split
+ * by input half, BatchNorm(eval) folded), W30_t[128][30] (pi|sigma|mu), b30[30]. Synchronous. */
+int b200dock_mdn_load_weights(B200Handle* h, const float* blob, size_t n);
+/* score: device [B]. */
+int b200dock_mdn_score(B200Handle* h, const B200MdnBatch* batch, float dist_threshold, float* score, void* stream);
+
 /* Introspection for tests / benchmarks: edge counts of the last evaluation
  * [E_ll, E_aa, E_al(=E_la), E_tor, E_sc], kernels launched by the last call, device time of the
  * dominant (tensor-product) kernel accumulated with CUDA events when profiling is enabled. */

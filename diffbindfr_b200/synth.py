@@ -300,3 +300,46 @@ def make_mdn_inputs(seed: int = 0, n_lig=(12, 30, 7), n_res=(20, 36, 11), missin
                 lig_pos=torch.randn(sum(nl), 3, generator=g) * 4, xyz_full=xyz,
                 lig_batch=torch.repeat_interleave(torch.arange(B), torch.tensor(nl)),
                 pro_batch=torch.repeat_interleave(torch.arange(B), torch.tensor(nr)))
+
+
+def make_mdn_complexes(seed: int = 0, n_lig=(12, 30, 7), n_res=(20, 36, 11), topk: int = 30) -> Dict[str, torch.Tensor]:
+    """Seeded, collated inputs of the whole MDN scorer forward (``KarmaDock.forward``):
+    synthetic pockets (``make_pocket``) featurised by ``mdn_features.protein_features``, synthetic ligands with the
+    reference's l2l edge layout (covalent edges first, then the remaining pairs of the complete graph,
+    ``ligand_feature.py:118-205``) and 0/1 node (89) / edge (20) features.  Flat keys, PyG-style collation
+    (node offsets added to the edge indices, ``*_batch`` vectors)."""
+    from . import mdn_features
+    rng = np.random.default_rng(seed)
+    keys = ("pro_node_s", "pro_node_v", "pro_edge_index", "pro_edge_s", "pro_edge_v", "pro_seq", "xyz_full", "pro_batch",
+            "lig_node_s", "lig_edge_s", "lig_edge_index", "lig_cov_edge_mask", "lig_pos", "lig_batch")
+    parts = {k: [] for k in keys}
+    r_off = l_off = 0
+    for b, (nl, nr) in enumerate(zip(n_lig, n_res)):
+        pk = make_pocket(rng, nr, 12.0 * max(nr / 36.0, 1.0) ** (1.0 / 3.0))
+        a14 = torch.from_numpy(pk["atom14_position"]).float()
+        m14 = torch.from_numpy(pk["atom14_mask"].astype(np.float32))
+        ang = torch.from_numpy(rng.uniform(-math.pi, math.pi, size=(nr, 3))).float()
+        f = mdn_features.protein_features(a14, m14, torch.stack([ang.sin(), ang.cos()], -1).reshape(nr, 6), topk)
+        parts["pro_node_s"].append(f["node_s"]); parts["pro_node_v"].append(f["node_v"])
+        parts["pro_edge_index"].append(f["edge_index"] + r_off); parts["pro_edge_s"].append(f["edge_s"]); parts["pro_edge_v"].append(f["edge_v"])
+        parts["pro_seq"].append(torch.from_numpy(pk["sequence"]).long()); parts["xyz_full"].append(a14)
+        parts["pro_batch"].append(torch.full((nr,), b, dtype=torch.long))
+        lg = make_ligand(rng, nl)
+        cov = torch.from_numpy(lg["lig_edge_index"]).long()
+        has = torch.zeros(nl, nl, dtype=torch.bool); has[cov[0], cov[1]] = True
+        rest = torch.nonzero(~has & ~torch.eye(nl, dtype=torch.bool)).T
+        ei = torch.cat([cov, rest], 1)
+        es = torch.zeros(ei.shape[1], 20)
+        es[:cov.shape[1]] = torch.from_numpy((rng.random((cov.shape[1], 20)) < 0.25).astype(np.float32))
+        es[cov.shape[1]:, [4, 5, 18]] = 1.0
+        parts["lig_node_s"].append(torch.from_numpy((rng.random((nl, 89)) < 0.15).astype(np.int32)))
+        parts["lig_edge_s"].append(es.int()); parts["lig_edge_index"].append(ei + l_off)
+        mask = torch.zeros(ei.shape[1], dtype=torch.bool); mask[:cov.shape[1]] = True
+        parts["lig_cov_edge_mask"].append(mask)
+        centre = a14[:, 1].mean(0)
+        parts["lig_pos"].append(torch.from_numpy(lg["lig_pos"]).float() - torch.from_numpy(lg["lig_pos"]).float().mean(0) + centre
+                                + torch.from_numpy(rng.normal(scale=2.0, size=3)).float())
+        parts["lig_batch"].append(torch.full((nl,), b, dtype=torch.long))
+        r_off += nr; l_off += nl
+    cat1 = ("pro_edge_index", "lig_edge_index")
+    return {k: torch.cat(v, 1 if k in cat1 else 0) for k, v in parts.items()}

@@ -239,3 +239,82 @@ def reference_sample_cfg():
                     eps=1e-5, no_final_step_noise=True, no_random=False, tr_sigma_min=0.1, tr_sigma_max=6,
                     rot_sigma_min=0.03, rot_sigma_max=1.55, tor_sigma_min=0.0314, tor_sigma_max=3.14,
                     sc_tor_sigma_min=0.0314, sc_tor_sigma_max=3.14)
+
+
+# ------------------------------------------------------------------------ MDN scorer (KarmaDock) shims
+class _MessagePassing(nn.Module):
+    """torch_geometric.nn.MessagePassing (2.2.0) restated for the one way GVP_Block.py:302-372 uses it:
+    ``propagate(edge_index, **tensors)`` -> ``message(<name>_i, <name>_j, ...)`` with ``_j = x[edge_index[0]]``,
+    ``_i = x[edge_index[1]]`` (flow source_to_target), aggregation over ``edge_index[1]``, 'mean' = sum / max(count, 1)."""
+
+    def __init__(self, aggr="add", **kw):
+        super().__init__()
+        self.aggr = aggr
+
+    def propagate(self, edge_index, size=None, **kwargs):
+        import inspect
+        n, args = None, {}
+        for p in inspect.signature(self.message).parameters:
+            if p.endswith("_i") or p.endswith("_j"):
+                t = kwargs[p[:-2]]
+                n = t.shape[0]
+                args[p] = t[edge_index[1] if p.endswith("_i") else edge_index[0]]
+            else:
+                args[p] = kwargs[p]
+        m = self.message(**args)
+        out = torch.zeros((n,) + tuple(m.shape[1:]), dtype=m.dtype).index_add_(0, edge_index[1], m)
+        if self.aggr == "mean":
+            cnt = torch.bincount(edge_index[1], minlength=n).clamp(min=1).to(m.dtype)
+            out = out / cnt[:, None]
+        return out
+
+
+class _GraphNorm(nn.Module):
+    """Constructible stand-in: KarmaDock builds ``GraphNorm(128)`` but the scoring forward never calls it."""
+
+    def __init__(self, c, eps=1e-5):
+        super().__init__()
+        self.weight, self.bias, self.mean_scale = nn.Parameter(torch.ones(c)), nn.Parameter(torch.zeros(c)), nn.Parameter(torch.ones(c))
+
+
+class _Store(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class HeteroData(dict):
+    """Just enough of torch_geometric.data.HeteroData for KarmaDock.forward: ``data['ligand'].x`` and
+    ``data['a', 'r', 'b'].y`` / ``data[('a', 'r', 'b')]['y']``."""
+
+    def __getitem__(self, k):
+        if k not in self:
+            dict.__setitem__(self, k, _Store())
+        return dict.__getitem__(self, k)
+
+
+def install_scoring(root: str = "/root/reference"):
+    """Make ``DiffBindFR.scoring.architecture.*`` importable from the reference tree (after ``install``)."""
+    install(root)
+    from .. import mdn as omdn
+    tgnn = importlib.import_module("torch_geometric.nn")
+    tgnn.MessagePassing, tgnn.GraphNorm = _MessagePassing, _GraphNorm
+    importlib.import_module("torch_geometric.utils").to_dense_batch = omdn.to_dense_batch
+    for name in ["DiffBindFR", "DiffBindFR.scoring", "DiffBindFR.scoring.architecture"]:
+        if name not in sys.modules:
+            p = _ThinPackage(name)
+            p.__path__ = [os.path.join(root, *name.split("."))]
+            sys.modules[name] = p
+
+
+def hetero_from_flat(x: Dict[str, torch.Tensor]) -> HeteroData:
+    """Flat dict of ``synth.make_mdn_complexes`` -> the HeteroData layout of pipeline.py:23-69 (collated)."""
+    d = HeteroData()
+    d["protein"].node_s, d["protein"].node_v, d["protein"].seq = x["pro_node_s"], x["pro_node_v"], x["pro_seq"]
+    d["protein"].xyz_full, d["protein"].batch = x["xyz_full"], x["pro_batch"]
+    e = d[("protein", "p2p", "protein")]
+    e.edge_index, e.edge_s, e.edge_v = x["pro_edge_index"], x["pro_edge_s"], x["pro_edge_v"]
+    d["ligand"].node_s, d["ligand"].xyz, d["ligand"].batch = x["lig_node_s"], x["lig_pos"], x["lig_batch"]
+    d["ligand"].cov_edge_mask = x["lig_cov_edge_mask"]
+    l = d[("ligand", "l2l", "ligand")]
+    l.edge_index, l.edge_s = x["lig_edge_index"], x["lig_edge_s"]
+    return d

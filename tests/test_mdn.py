@@ -47,3 +47,39 @@ def test_cuda_mdn_threshold_and_empty_contacts():
     sc = MDNScorer(Engine(0)); sc.load_state_dict(weights.random_mdn_state_dict(0))
     out = sc.scoring(x["lig_s"], x["lig_pos"], x["lig_batch"], x["pro_s"], x["xyz_full"], x["pro_batch"])
     assert torch.count_nonzero(out.cpu()) == 0
+
+
+# ------------------------------------------------------------------ whole scorer forward (encoders + head)
+FULL_TAGS = ["small", "cfgA", "ragged"]
+
+
+@pytest.mark.parametrize("tag", FULL_TAGS)
+def test_oracle_karmadock_matches_reference_fixture(tag):
+    """O2 (oracle/mdn_encoders.py) against the output of the reference's own KarmaDock_sc.py / GVP_Block.py /
+    GraphTransformer_Block.py / MDN_Block.py run on the shims (tools/make_golden_mdn.py)."""
+    from oracle import mdn_encoders as oenc
+    g = load_golden("mdn_full.pt")[tag]
+    x = synth.make_mdn_complexes(**g["kwargs"])
+    sd = weights.random_karmadock_state_dict(0)
+    pro_s, lig_s = oenc.encoding(sd, x)
+    assert torch.allclose(pro_s, g["pro_s"], rtol=1e-5, atol=2e-6)
+    assert torch.allclose(lig_s, g["lig_s"], rtol=1e-5, atol=2e-6)
+    assert torch.allclose(oenc.karmadock_forward(sd, x), g["score"], rtol=1e-5, atol=1e-6)
+
+
+def test_knn_graph_restatement():
+    from diffbindfr_b200 import mdn_features
+    x = torch.tensor([[0.0, 0, 0], [1.0, 0, 0], [3.0, 0, 0], [7.0, 0, 0]])
+    ei = mdn_features.knn_graph(x, 2)
+    assert ei[1].tolist() == [0, 0, 1, 1, 2, 2, 3, 3]            # centres ascending
+    assert ei[0].tolist() == [1, 2, 0, 2, 1, 0, 2, 1]            # neighbours by ascending distance, no self loops
+    assert mdn_features.knn_graph(x, 30).shape == (2, 12)        # fewer than k nodes: all others
+
+
+def test_karmadock_state_dict_contract():
+    keys = [k for k, _, _ in weights.karmadock_param_shapes()]
+    assert len(keys) == len(set(keys))
+    sd = weights.random_karmadock_state_dict(0)
+    assert sd["pro_encoder.layers.2.conv.message_func.0.ws.weight"].shape == (128, 321)
+    assert sd["lig_encoder.gt_block.5.node_feats_MLP.3.weight"].shape == (128, 256)
+    assert "lig_encoder.gt_block.5.O_edge_feats.weight" not in sd and "mdn_layer.z_mu.bias" in sd

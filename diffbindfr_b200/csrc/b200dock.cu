@@ -16,6 +16,7 @@
 #include "heads.cuh"
 #include "pose.cuh"
 #include "mdn.cuh"
+#include "mdn_enc.cuh"
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -63,6 +64,7 @@ struct B200Handle {
   Buf pre[6], h_lig, h_atom, jmax_lig, jmax_atom, centre, cmsg, s_tr, s_rot, s_tor, s_sc, atom14, errflag;
   Buf c_temb, c_trs, c_rotn, c_torn, c_scn, temb_steps;
   Buf mdn_w, mdn_A, mdn_B; bool mdn_weights = false;
+  Buf enc_w, enc_ws; std::vector<int64_t> enc_off; bool enc_weights = false;
   // host-batch path
   Buf pinned_in, dev_in, dev_noise, dev_lig_out, dev_a14_out, pinned_out;
   int64_t launches = 0;
@@ -521,7 +523,7 @@ void b200dock_destroy(B200Handle* h) {
   for (auto& b : h->pre) fr(b);
   Buf* all[] = {&h->h_lig, &h->h_atom, &h->jmax_lig, &h->jmax_atom, &h->centre, &h->cmsg, &h->s_tr, &h->s_rot, &h->s_tor,
                 &h->s_sc, &h->atom14, &h->errflag, &h->c_temb, &h->c_trs, &h->c_rotn, &h->c_torn, &h->c_scn,
-                &h->temb_steps, &h->mdn_w, &h->mdn_A, &h->mdn_B, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
+                &h->temb_steps, &h->mdn_w, &h->mdn_A, &h->mdn_B, &h->enc_w, &h->enc_ws, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
   for (Buf* b : all) fr(*b);
   if (h->pinned_in.p) cudaFreeHost(h->pinned_in.p);
   if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
@@ -749,6 +751,138 @@ int b200dock_mdn_score(B200Handle* h, const B200MdnBatch* mb, float dist_thresho
   M.xyz_full = mb->xyz_full; M.res_ptr = mb->res_ptr; M.W30t = W30; M.b30 = b30; M.thr = dist_threshold; M.score = score;
   k_mdn_pairs<<<grid_for(mb->B, 1, 148 * 4), 256, 0, st>>>(M);
   h->launches += 3;
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200dock_mdn_load_encoder_weights(B200Handle* h, const float* blob, size_t n, const int64_t* offsets, int n_offsets) {
+  if (!h || !blob || !offsets) return B200_ERR_INVALID;
+  if (n_offsets != B200_MDN_ENC_SECTIONS) FAIL(B200_ERR_INVALID, "unexpected number of MDN encoder weight sections");
+  for (int i = 0; i < n_offsets; ++i)
+    if (offsets[i] < -1 || offsets[i] >= (int64_t)n) FAIL(B200_ERR_INVALID, "MDN encoder weight offset out of range");
+  CK(cudaSetDevice(h->device));
+  ENS(h->enc_w, n * sizeof(float));
+  CK(cudaMemcpy(h->enc_w.p, blob, n * sizeof(float), cudaMemcpyHostToDevice));
+  h->enc_off.assign(offsets, offsets + n_offsets);
+  h->enc_weights = true;
+  return B200_OK;
+}
+
+namespace {
+struct EncCtx {
+  B200Handle* h; cudaStream_t st; const float* W;
+  const float* sec(int i) const { return h->enc_off[i] < 0 ? nullptr : W + h->enc_off[i]; }
+  void linear(const float* in, int ld_in, int rows, int K, int O, int wsec, int bsec, int act, const float* res, float* out) const {
+    LinArgs A{in, ld_in, rows, K, O, sec(wsec), bsec >= 0 ? sec(bsec) : nullptr, act, res, O, out, O};
+    k_enc_linear<<<grid_for(rows, ENC_ROWS, 148 * 8), ENC_THREADS, (size_t)ENC_ROWS * K * 4, st>>>(A);
+    h->launches++;
+  }
+  // GVP with weight sections [base, base+4); segments given by the caller
+  void gvp(GvpArgs A, int base, int scalar_act, int vector_act) const {
+    A.h = A.vi > A.vo ? A.vi : A.vo;
+    A.wh = sec(base); A.ws_t = sec(base + 1); A.ws_b = sec(base + 2); A.wv = sec(base + 3);
+    A.scalar_act = scalar_act; A.vector_act = vector_act;
+    const size_t sm = (size_t)ENC_ROWS * (A.si + A.h + 3 * A.vi + 3 * A.h) * 4;
+    k_gvp<<<grid_for(A.rows, ENC_ROWS, 148 * 8), ENC_THREADS, sm, st>>>(A);
+    h->launches++;
+  }
+  void ln(GvpLnArgs A, int base) const {
+    A.w = sec(base); A.b = sec(base + 1);
+    k_gvp_ln<<<grid_for(A.rows, 4, 148 * 8), 128, 0, st>>>(A);
+    h->launches++;
+  }
+};
+GvpArgs gvp_plain(int rows, int si, int vi, int so, int vo, const float* s, const float* v, float* os, float* ov) {
+  GvpArgs A{};
+  A.rows = rows; A.si = si; A.vi = vi; A.so = so; A.vo = vo;
+  A.s[0] = GvpSeg{s, nullptr, si}; A.v[0] = GvpSeg{v, nullptr, vi};
+  A.out_s = os; A.out_v = ov;
+  return A;
+}
+}  // namespace
+
+int b200dock_mdn_encode(B200Handle* h, const B200MdnGraph* g, float* pro_s, float* lig_s, void* stream) {
+  if (!h || !g || !pro_s || !lig_s) return B200_ERR_INVALID;
+  if (!h->enc_weights) FAIL(B200_ERR_STATE, "MDN encoder weights not loaded");
+  if (g->N_r <= 0 || g->N_l <= 0 || g->E_p < 0 || g->E_l < 0) FAIL(B200_ERR_INVALID, "empty MDN graph");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t Nl = g->N_l, El = g->E_l > 0 ? g->E_l : 1, Nr = g->N_r, Ep = g->E_p > 0 ? g->E_p : 1;
+  // workspace carve-up (floats)
+  size_t need = 0;
+  auto take = [&](size_t n) { size_t o = need; need += (n + 63) & ~(size_t)63; return o; };
+  // ligand
+  const size_t o_x = take(Nl * 128), o_x2 = take(Nl * 128), o_qkv = take(Nl * 384), o_hn = take(Nl * 128), o_t256 = take(Nl * 256);
+  const size_t o_e = take(El * 128), o_e2 = take(El * 128), o_ep = take(El * 128), o_al = take(El * 128), o_ax = take(El * 4), o_et = take(El * 256);
+  // pocket
+  const size_t o_s0 = take(Nr * 40), o_v0 = take(Nr * 9), o_s = take(Nr * 128), o_v = take(Nr * 48), o_sb = take(Nr * 128), o_vb = take(Nr * 48);
+  const size_t o_ds = take(Nr * 128), o_dv = take(Nr * 48), o_fs = take(Nr * 512), o_fv = take(Nr * 96);
+  const size_t o_es0 = take(Ep * 21), o_ev0 = take(Ep * 3), o_es = take(Ep * 32), o_ev = take(Ep * 3);
+  const size_t o_ms = take(Ep * 128), o_mv = take(Ep * 48), o_ms2 = take(Ep * 128), o_mv2 = take(Ep * 48);
+  ENS(h->enc_ws, need * 4);
+  float* ws = h->enc_ws.as<float>();
+  EncCtx C{h, st, h->enc_w.as<float>()};
+
+  // ======================= ligand graph transformer (GraphTransformer_Block.py:413-424)
+  float *x = ws + o_x, *x2 = ws + o_x2, *e = ws + o_e, *e2 = ws + o_e2;
+  C.linear(g->lig_node_s, 89, g->N_l, 89, 128, 0, 1, 0, nullptr, x);
+  if (g->E_l > 0) C.linear(g->lig_edge_s, 20, g->E_l, 20, 128, 2, 3, 0, nullptr, e);
+  for (int l = 0; l < 6; ++l) {
+    const int b = 4 + 14 * l;
+    const bool fin = l == 5;
+    C.linear(x, 128, g->N_l, 128, 384, b, b + 1, 0, nullptr, ws + o_qkv);                       // BN1 folded: Q | K | V
+    if (g->E_l > 0) {
+      C.linear(e, 128, g->E_l, 128, 128, b + 2, b + 3, 0, nullptr, ws + o_ep);                   // BN1 folded: edge projection
+      k_gt_edge<<<grid_for(g->E_l, 8, 148 * 8), 256, 0, st>>>(ws + o_qkv, ws + o_ep, g->lig_row, g->lig_col, g->E_l, ws + o_al, ws + o_ax);
+      h->launches++;
+    }
+    k_gt_node<<<grid_for(g->N_l, 1, 148 * 8), 128, 0, st>>>(ws + o_qkv, ws + o_ax, g->lig_row, g->lig_perm, g->lig_ptr, g->N_l, ws + o_hn);
+    h->launches++;
+    C.linear(ws + o_hn, 128, g->N_l, 128, 128, b + 4, b + 5, 0, x, x2);                          // x2 = x + O_node(h)
+    C.linear(x2, 128, g->N_l, 128, 256, b + 6, b + 7, 1, nullptr, ws + o_t256);                  // BN2 folded, SiLU
+    C.linear(ws + o_t256, 256, g->N_l, 256, 128, b + 8, -1, 0, x2, fin ? lig_s : x);             // x = x2 + MLP
+    if (!fin && g->E_l > 0) {
+      C.linear(ws + o_al, 128, g->E_l, 128, 128, b + 9, b + 10, 0, e, e2);
+      C.linear(e2, 128, g->E_l, 128, 256, b + 11, b + 12, 1, nullptr, ws + o_et);
+      C.linear(ws + o_et, 256, g->E_l, 256, 128, b + 13, -1, 0, e2, e);
+    }
+  }
+
+  // ======================= pocket GVP embedding (GVP_Block.py:63-79)
+  float *s = ws + o_s, *v = ws + o_v, *sb = ws + o_sb, *vb = ws + o_vb;
+  {
+    GvpLnArgs L{}; L.rows = g->N_r; L.ns = 40; L.nv = 3; L.s = g->pro_node_s; L.v = g->pro_node_v; L.emb = C.sec(88); L.seq = g->pro_seq; L.ns0 = 9;
+    L.out_s = ws + o_s0; L.out_v = ws + o_v0;
+    C.ln(L, 89);
+    C.gvp(gvp_plain(g->N_r, 40, 3, 128, 16, ws + o_s0, ws + o_v0, s, v), 91, 0, 0);
+  }
+  if (g->E_p > 0) {
+    GvpLnArgs L{}; L.rows = g->E_p; L.ns = 21; L.nv = 1; L.s = g->pro_edge_s; L.v = g->pro_edge_v; L.out_s = ws + o_es0; L.out_v = ws + o_ev0;
+    C.ln(L, 95);
+    C.gvp(gvp_plain(g->E_p, 21, 1, 32, 1, ws + o_es0, ws + o_ev0, ws + o_es, ws + o_ev), 97, 0, 0);
+  }
+  for (int l = 0; l < 3; ++l) {
+    const int b = 101 + 24 * l;
+    if (g->E_p > 0) {
+      GvpArgs M{};
+      M.rows = g->E_p; M.si = 288; M.vi = 33; M.so = 128; M.vo = 16;
+      M.s[0] = GvpSeg{s, g->pro_src, 128}; M.s[1] = GvpSeg{ws + o_es, nullptr, 32}; M.s[2] = GvpSeg{s, g->pro_dst, 128};
+      M.v[0] = GvpSeg{v, g->pro_src, 16};  M.v[1] = GvpSeg{ws + o_ev, nullptr, 1};  M.v[2] = GvpSeg{v, g->pro_dst, 16};
+      M.out_s = ws + o_ms; M.out_v = ws + o_mv;
+      C.gvp(M, b, 1, 1);
+      C.gvp(gvp_plain(g->E_p, 128, 16, 128, 16, ws + o_ms, ws + o_mv, ws + o_ms2, ws + o_mv2), b + 4, 1, 1);
+      C.gvp(gvp_plain(g->E_p, 128, 16, 128, 16, ws + o_ms2, ws + o_mv2, ws + o_ms, ws + o_mv), b + 8, 0, 0);
+    }
+    k_seg_mean<<<grid_for(g->N_r, 1, 148 * 8), 128, 0, st>>>(ws + o_ms, 128, g->pro_perm, g->pro_ptr, g->N_r, ws + o_ds);
+    k_seg_mean<<<grid_for(g->N_r, 1, 148 * 8), 64, 0, st>>>(ws + o_mv, 48, g->pro_perm, g->pro_ptr, g->N_r, ws + o_dv);
+    h->launches += 2;
+    { GvpLnArgs L{}; L.rows = g->N_r; L.ns = 128; L.nv = 16; L.s = s; L.v = v; L.ds = ws + o_ds; L.dv = ws + o_dv; L.out_s = sb; L.out_v = vb; C.ln(L, b + 12); }
+    C.gvp(gvp_plain(g->N_r, 128, 16, 512, 32, sb, vb, ws + o_fs, ws + o_fv), b + 14, 1, 1);
+    C.gvp(gvp_plain(g->N_r, 512, 32, 128, 16, ws + o_fs, ws + o_fv, ws + o_ds, ws + o_dv), b + 18, 0, 0);
+    { GvpLnArgs L{}; L.rows = g->N_r; L.ns = 128; L.nv = 16; L.s = sb; L.v = vb; L.ds = ws + o_ds; L.dv = ws + o_dv; L.out_s = s; L.out_v = v; C.ln(L, b + 22); }
+  }
+  { GvpLnArgs L{}; L.rows = g->N_r; L.ns = 128; L.nv = 16; L.s = s; L.v = v; L.out_s = sb; L.out_v = vb; C.ln(L, 173); }
+  C.gvp(gvp_plain(g->N_r, 128, 16, 128, 0, sb, vb, pro_s, nullptr), 175, 1, 0);
   CK(cudaGetLastError());
   return B200_OK;
 }

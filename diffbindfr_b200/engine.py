@@ -24,7 +24,8 @@ EXPORTS = ["b200dock_create", "b200dock_destroy", "b200dock_last_error", "b200do
            "b200dock_load_weights", "b200dock_score", "b200dock_sample", "b200dock_sample_host",
            "b200dock_last_edge_counts", "b200dock_last_launch_count", "b200dock_set_profiling",
            "b200dock_tp_kernel_time_ms", "b200dock_debug_tap", "b200dock_debug_set",
-           "b200dock_mdn_load_weights", "b200dock_mdn_score"]
+           "b200dock_mdn_load_weights", "b200dock_mdn_score",
+           "b200dock_mdn_load_encoder_weights", "b200dock_mdn_encode"]
 
 
 class CCond(C.Structure):
@@ -65,6 +66,8 @@ def load_library(path: Optional[str] = None):
     lib.b200dock_debug_set.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.b200dock_mdn_load_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.b200dock_mdn_score.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    lib.b200dock_mdn_load_encoder_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.b200dock_mdn_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if path is None:
         _lib = lib
     return lib

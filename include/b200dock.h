@@ -211,7 +211,7 @@ int b200dock_sample_host(B200Handle* h, const B200Batch* host_batch, const B200S
 
 /* MDN scoring head: KarmaDock.scoring(lig_s, lig_pos, pro_s, data, dist_threhold, batch_size)
  * (DiffBindFR/scoring/architecture/KarmaDock_sc.py:87-101, MDN_Block.py:20-79; called from
- * DiffBindFR/common/engines.py:285-294).  The encoders producing lig_s / pro_s are not part of the library yet. */
+ * DiffBindFR/common/engines.py:285-294).  lig_s / pro_s come from b200dock_mdn_encode. */
 typedef struct {
   int32_t B, N_l, N_r;
   const float* lig_s;             /* [N_l][128] ligand atom embeddings */
@@ -226,6 +226,45 @@ typedef struct {
 int b200dock_mdn_load_weights(B200Handle* h, const float* blob, size_t n);
 /* score: device [B]. */
 int b200dock_mdn_score(B200Handle* h, const B200MdnBatch* batch, float dist_threshold, float* score, void* stream);
+
+/* MDN scorer encoders: KarmaDock.encoding(data) -> (pro_node_s, lig_node_s)
+ * (DiffBindFR/scoring/architecture/KarmaDock_sc.py:71-85; GVP_Block.py:63-79 GVP_embedding.forward,
+ * GraphTransformer_Block.py:413-424 GraghTransformer.forward; called from DiffBindFR/common/engines.py:285).
+ * All pointers are device pointers owned by the caller; indices are int32.  The ligand edges are the covalent subset
+ * (the reference indexes edge_s / edge_index with cov_edge_mask before the encoder).  (perm, ptr) is the CSR of the edges
+ * by aggregation target in stable edge order: ligand target = col (edge_index[1]), pocket target = dst (edge_index[1]). */
+typedef struct {
+  int32_t N_r, E_p, N_l, E_l;
+  const float* pro_node_s;        /* [N_r][9] */
+  const float* pro_node_v;        /* [N_r][3][3] */
+  const int32_t* pro_seq;         /* [N_r] residue type, 0..30 */
+  const int32_t* pro_src;         /* [E_p] edge_index[0] (message source j) */
+  const int32_t* pro_dst;         /* [E_p] edge_index[1] (target i) */
+  const float* pro_edge_s;        /* [E_p][21] */
+  const float* pro_edge_v;        /* [E_p][1][3] */
+  const int32_t* pro_perm;        /* [E_p] */
+  const int32_t* pro_ptr;         /* [N_r+1] */
+  const float* lig_node_s;        /* [N_l][89] */
+  const float* lig_edge_s;        /* [E_l][20] */
+  const int32_t* lig_row;         /* [E_l] edge_index[0] */
+  const int32_t* lig_col;         /* [E_l] edge_index[1] */
+  const int32_t* lig_perm;        /* [E_l] */
+  const int32_t* lig_ptr;         /* [N_l+1] */
+} B200MdnGraph;
+/* Encoder weights: one fp32 blob + B200_MDN_ENC_SECTIONS offsets (in floats, -1 = section absent), packed by
+ * diffbindfr_b200/mdn.py::pack_encoder_weights.  Linear weights are stored transposed [in][out]; BatchNorm1d(eval)
+ * is folded into the Linear that follows it.  Section order:
+ *   0..3    graph transformer node_encoder W,b; edge_encoder W,b
+ *   4+14l+j layer l<6: QKV W[128][384],b; edge proj W,b; O_node W,b; node MLP.0 W[128][256],b; node MLP.3 W[256][128];
+ *           O_edge W,b; edge MLP.0 W,b; edge MLP.3 W   (edge sections absent in the final layer)
+ *   88      W_s embedding [31][31];  89,90 W_v LayerNorm w,b;  91..94 W_v GVP (wh[h][vi], ws_t[si+h][so], ws_b, wv[vo][h])
+ *   95,96   W_e LayerNorm;  97..100 W_e GVP
+ *   101+24l layer l<3: message GVP 0,1,2 (4 each), norm.0 (2), ff GVP 0,1 (4 each), norm.1 (2)
+ *   173,174 W_out LayerNorm;  175..178 W_out GVP (wv absent) */
+#define B200_MDN_ENC_SECTIONS 179
+int b200dock_mdn_load_encoder_weights(B200Handle* h, const float* blob, size_t n, const int64_t* offsets, int n_offsets);
+/* pro_s: device [N_r][128]; lig_s: device [N_l][128]. Asynchronous on `stream`. */
+int b200dock_mdn_encode(B200Handle* h, const B200MdnGraph* g, float* pro_s, float* lig_s, void* stream);
 
 /* Introspection for tests / benchmarks: edge counts of the last evaluation
  * [E_ll, E_aa, E_al(=E_la), E_tor, E_sc], kernels launched by the last call, device time of the

@@ -83,3 +83,47 @@ def test_karmadock_state_dict_contract():
     assert sd["pro_encoder.layers.2.conv.message_func.0.ws.weight"].shape == (128, 321)
     assert sd["lig_encoder.gt_block.5.node_feats_MLP.3.weight"].shape == (128, 256)
     assert "lig_encoder.gt_block.5.O_edge_feats.weight" not in sd and "mdn_layer.z_mu.bias" in sd
+
+
+def test_encoder_weight_packing_folds_batchnorm():
+    from diffbindfr_b200 import mdn as bmdn
+    sd = weights.random_karmadock_state_dict(0)
+    blob, off = bmdn.pack_encoder_weights(sd)
+    assert off.shape == (bmdn.ENC_SECTIONS,) and (off[[4 + 14 * 5 + j for j in range(9, 14)]] == -1).all() and off[178] == -1
+    # folded QKV of layer 0 applied to x equals Q/K/V(BN(x))
+    x = torch.randn(5, 128)
+    p = "lig_encoder.gt_block.0."
+    bn = (x - sd[p + "batch_norm1_node_feats.running_mean"]) / torch.sqrt(sd[p + "batch_norm1_node_feats.running_var"] + 1e-5) \
+        * sd[p + "batch_norm1_node_feats.weight"] + sd[p + "batch_norm1_node_feats.bias"]
+    ref = torch.cat([bn @ sd[p + f"mha_module.{n}.weight"].T for n in "QKV"], 1)
+    Wt = torch.from_numpy(blob[off[4]:off[4] + 128 * 384]).view(128, 384)
+    b = torch.from_numpy(blob[off[5]:off[5] + 384])
+    assert torch.allclose(x @ Wt + b, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", FULL_TAGS)
+def test_cuda_karmadock_matches_reference_fixture(tag):
+    """CUDA encoders + head through the C ABI against the reference-generated fixture (fp32; different summation
+    order than torch's GEMMs: 1e-4 on the 128-d embeddings after 6 / 3 message-passing layers, 1e-4 relative on scores)."""
+    from diffbindfr_b200.engine import Engine
+    from diffbindfr_b200.mdn import MDNScorer
+    g = load_golden("mdn_full.pt")[tag]
+    x = synth.make_mdn_complexes(**g["kwargs"])
+    sc = MDNScorer(Engine(0))
+    sc.load_state_dict(weights.random_karmadock_state_dict(0))
+    pro_s, lig_s = sc.encoding(x)
+    score = sc(x)
+    torch.cuda.synchronize()
+    assert torch.allclose(pro_s.cpu(), g["pro_s"], rtol=1e-4, atol=1e-4), (pro_s.cpu() - g["pro_s"]).abs().max()
+    assert torch.allclose(lig_s.cpu(), g["lig_s"], rtol=1e-4, atol=1e-4), (lig_s.cpu() - g["lig_s"]).abs().max()
+    assert torch.allclose(score.cpu(), g["score"], rtol=1e-4, atol=1e-5), (score.cpu(), g["score"])
+
+
+@pytest.mark.gpu
+def test_cuda_encoders_require_weights():
+    from diffbindfr_b200.engine import Engine
+    from diffbindfr_b200.mdn import MDNScorer
+    sc = MDNScorer(Engine(0))
+    with pytest.raises(RuntimeError):
+        sc.encoding(synth.make_mdn_complexes(seed=1))

@@ -169,8 +169,9 @@ class DiffBindFR(nn.Module):
     def __init__(self, diffusion_model: Optional[dict] = None, scoring_model: Optional[dict] = None,
                  train_cfg: dict = {}, test_cfg: dict = {}, pretrained=None, init_cfg: dict = {}, **kwargs):
         super().__init__()
-        if scoring_model is not None:
-            raise NotImplementedError("the MDN scoring model is not part of the B200 plugin yet (SURVEY.md 8(a) row a21)")
+        # scFlex.py:43-46 builds `scoring_model` through the ENERGY registry; the shipped config leaves it None and
+        # drives the MDN scorer separately (common.engines.Scorer).  Here a non-None cfg builds the device KarmaDock.
+        self.scoring_model = KarmaDock() if scoring_model is not None else None
         if diffusion_model is not None:
             self.diffusion_model_cfg = copy.deepcopy(_get(diffusion_model, "cfg"))
             dm = diffusion_model
@@ -240,6 +241,73 @@ class DiffBindFR(nn.Module):
         for g in range(B):
             out.append((lig_t[:, lb == g], a14_t[:, res_b == g]))
         return out
+
+
+def _flat_mdn_inputs(data) -> Dict[str, torch.Tensor]:
+    """HeteroData of ``scoring/dataset/pipeline.py:23-69`` (or the flat dict of ``synth.make_mdn_complexes``) -> flat dict."""
+    if isinstance(data, dict) and "pro_node_s" in data:
+        return data
+    pr, lg = data["protein"], data["ligand"]
+    pp, ll = data[("protein", "p2p", "protein")], data[("ligand", "l2l", "ligand")]
+    return dict(pro_node_s=_get(pr, "node_s"), pro_node_v=_get(pr, "node_v"), pro_seq=_get(pr, "seq"), xyz_full=_get(pr, "xyz_full"),
+                pro_batch=_get(pr, "batch"), pro_edge_index=_get(pp, "edge_index"), pro_edge_s=_get(pp, "edge_s"),
+                pro_edge_v=_get(pp, "edge_v"), lig_node_s=_get(lg, "node_s"), lig_pos=_get(lg, "xyz"), lig_batch=_get(lg, "batch"),
+                lig_cov_edge_mask=_get(lg, "cov_edge_mask"), lig_edge_index=_get(ll, "edge_index"), lig_edge_s=_get(ll, "edge_s"))
+
+
+class KarmaDock(nn.Module):
+    """MDN scorer (``DiffBindFR/scoring/architecture/KarmaDock_sc.py:14-101``) on the device.  Same call surface as
+    the reference module that ``common.engines.Scorer`` drives (``engines.py:246-294``): ``encoding(data)``,
+    ``scoring(lig_s, lig_pos, pro_s, data, dist_threhold, batch_size)``, ``forward(data)``; parameters carry the
+    reference's names for ``lig_encoder.*``, ``pro_encoder.*`` and ``mdn_layer.{MLP,z_pi,z_sigma,z_mu}.*``.  The
+    reference loads its checkpoint with ``strict=False`` (``engines.py:264-269``): keys of the modules the scoring
+    forward never executes (EGNN pose head, gates, GraphNorm, AngleResnet, atom/bond type heads) are ignored here."""
+
+    def __init__(self, device: Optional[int] = None):
+        super().__init__()
+        from . import weights as _w
+        for k, v in _w.random_karmadock_state_dict(0).items():
+            _attach(self, k, v.clone(), buffer=not v.is_floating_point() or "running_" in k)
+        self._device_index = device
+        self._scorer = None
+        self._packed = False
+
+    def load_state_dict(self, state_dict, strict: bool = False, **kw):
+        own = set(self.state_dict().keys())
+        sd = {k: v for k, v in state_dict.items() if k in own}
+        missing = own - set(sd)
+        if strict and missing:
+            raise RuntimeError(f"missing keys in the MDN scorer checkpoint: {sorted(missing)[:5]} ...")
+        out = super().load_state_dict(sd, strict=False, **kw)
+        self._packed = False
+        return out
+
+    def scorer(self):
+        from .mdn import MDNScorer
+        if not torch.cuda.is_available():
+            raise RuntimeError("KarmaDockB200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if self._scorer is None:
+            dev = self._device_index if self._device_index is not None else torch.cuda.current_device()
+            self._scorer = MDNScorer(Engine(dev))
+        if not self._packed:
+            self._scorer.load_state_dict({k: v.detach().cpu() for k, v in self.state_dict().items()})
+            self._packed = True
+        return self._scorer
+
+    @torch.no_grad()
+    def encoding(self, data):
+        return self.scorer().encoding(_flat_mdn_inputs(data))
+
+    @torch.no_grad()
+    def scoring(self, lig_s, lig_pos, pro_s, data, dist_threhold, batch_size):
+        x = _flat_mdn_inputs(data)
+        return self.scorer().scoring(lig_s, lig_pos, x["lig_batch"], pro_s, x["xyz_full"], x["pro_batch"], float(dist_threhold))
+
+    @torch.no_grad()
+    def forward(self, data):
+        x = _flat_mdn_inputs(data)
+        pro_s, lig_s = self.encoding(x)
+        return self.scoring(lig_s, x["lig_pos"], pro_s, x, 5.0, int(x["lig_batch"][-1]) + 1)
 
 
 def register(force: bool = True) -> bool:

@@ -29,8 +29,8 @@ def test_plugin_state_dict_matches_reference_contract():
 def test_plugin_rejects_unsupported_architecture():
     with pytest.raises(NotImplementedError):
         plugin.TensorProductModel(dict(ns=32))
-    with pytest.raises(NotImplementedError):
-        plugin.DiffBindFR(diffusion_model=dict(cfg=None), scoring_model=dict(cfg={}))
+    m = plugin.DiffBindFR(diffusion_model=None, scoring_model=dict(cfg={}))      # builds the device MDN scorer
+    assert isinstance(m.scoring_model, plugin.KarmaDock)
 
 
 @pytest.mark.reference
@@ -102,3 +102,48 @@ def test_two_rank_gloo_shard_and_gather():
     res = [q.get(timeout=120) for _ in ps]
     [p.join(timeout=60) for p in ps]
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_karmadock_plugin_state_dict_contract():
+    """The device scorer exposes the reference's parameter names and, like ``Scorer`` (engines.py:264-269,
+    strict=False), ignores checkpoint keys of modules the scoring forward never runs."""
+    from diffbindfr_b200 import plugin, weights
+    m = plugin.KarmaDock()
+    want = {k for k, _, _ in weights.karmadock_param_shapes()} | set(weights.random_mdn_state_dict(0))
+    assert set(m.state_dict().keys()) == want
+    sd = weights.random_karmadock_state_dict(3)
+    sd["egnn_layers.0.q_layer.weight"] = torch.zeros(128, 128)      # extra key of the pose head: ignored
+    m.load_state_dict(sd)
+    assert torch.equal(m.state_dict()["pro_encoder.W_out.1.ws.weight"], sd["pro_encoder.W_out.1.ws.weight"])
+    del sd["mdn_layer.z_pi.weight"]
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(sd, strict=True)
+
+
+def test_karmadock_plugin_has_no_cpu_fallback():
+    from diffbindfr_b200 import plugin, synth
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        plugin.KarmaDock()(synth.make_mdn_complexes(seed=1, n_lig=(5,), n_res=(6,)))
+
+
+@pytest.mark.gpu
+def test_karmadock_plugin_forward_heterodata_layout():
+    """HeteroData-style access (data['ligand'].xyz, data[('protein','p2p','protein')]) through the plugin == fixture."""
+    from diffbindfr_b200 import plugin, synth, weights
+    from helpers import load_golden
+
+    class Store(dict):
+        __getattr__ = dict.__getitem__
+
+    g = load_golden("mdn_full.pt")["small"]
+    x = synth.make_mdn_complexes(**g["kwargs"])
+    data = {"protein": Store(node_s=x["pro_node_s"], node_v=x["pro_node_v"], seq=x["pro_seq"], xyz_full=x["xyz_full"], batch=x["pro_batch"]),
+            "ligand": Store(node_s=x["lig_node_s"], xyz=x["lig_pos"], batch=x["lig_batch"], cov_edge_mask=x["lig_cov_edge_mask"]),
+            ("protein", "p2p", "protein"): Store(edge_index=x["pro_edge_index"], edge_s=x["pro_edge_s"], edge_v=x["pro_edge_v"]),
+            ("ligand", "l2l", "ligand"): Store(edge_index=x["lig_edge_index"], edge_s=x["lig_edge_s"])}
+    m = plugin.KarmaDock()
+    m.load_state_dict(weights.random_karmadock_state_dict(0))
+    out = m(data)
+    assert torch.allclose(out.cpu(), g["score"], rtol=1e-4, atol=1e-5)

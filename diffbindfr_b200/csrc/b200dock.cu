@@ -13,6 +13,7 @@
 #include "conv.cuh"
 #include "conv_tc.cuh"
 #include "conv_fused.cuh"
+#include "conv_fused2.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
 #include "mdn.cuh"
@@ -207,13 +208,13 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
-  if (h->cfg.conv_kernel == 5) {
+  if (h->cfg.conv_kernel >= 5) {
     Fused16Extra F{};
     for (int i = 0; i < L.n; ++i) {
       F.W1hi[i] = X.W1h16[i]; F.W1lo[i] = X.W1l16[i]; F.W2hi[i] = X.W2h16[i]; F.W2lo[i] = X.W2l16[i];
       F.w2_rows[i] = X.w2_rows[i] + 144;
     }
-    rc = launch_conv_fused16(L, F, h->tp_grid, st);
+    rc = h->cfg.conv_kernel == 6 ? launch_conv_fused16x2(L, F, h->tp_grid, st) : launch_conv_fused16(L, F, h->tp_grid, st);
   } else if (h->cfg.conv_kernel == 4) {
     FusedExtra F{};
     for (int i = 0; i < L.n; ++i) { F.W1hi[i] = X.W1hi[i]; F.W1lo[i] = X.W1lo[i]; F.W2lo[i] = X.W2_lo[i]; F.w2_rows[i] = X.w2_rows[i]; }
@@ -509,7 +510,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
   CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
   CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
-  if (conv_tc_init() || conv_fused_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  if (conv_tc_init() || conv_fused_init() || conv_fused2_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
   h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
   return B200_OK;
 }
@@ -588,7 +589,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     }
     CK(cudaDeviceSynchronize());
   }
-  if (h->cfg.conv_kernel == 5) {   // fp16 hi/lo copies of W1p / W2p with exact power-of-two scales
+  if (h->cfg.conv_kernel >= 5) {   // fp16 hi/lo copies of W1p / W2p with exact power-of-two scales
     size_t tot = 0;
     for (int i = 0; i < 26; ++i) tot += ((size_t)h->convw[i].n_cols + 144 + 192) * KH;
     if (h->d_w16) CK(cudaFree(h->d_w16));

@@ -106,7 +106,8 @@ class Engine:
     """One handle = one device.  ``conv_kernel``: 0 SIMT fp32 (exact), 1 tcgen05 3xTF32 (H1 in smem),
     2 tcgen05 single TF32 (fast, ~1e-3), 3 tcgen05 3xTF32 with H1 resident in tensor memory,
     4 fully fused tcgen05 3xTF32 conv (both FC layers + fold in one kernel),
-    5 the fused kernel with FP16 hi/lo error-compensated MMAs and per-row scaling (default, fp32-grade)."""
+    5 the fused kernel with FP16 hi/lo error-compensated MMAs and per-row scaling (fp32-grade),
+    6 mode 5 on CTA pairs (tcgen05 cta_group::2: the weight operand is split across two SMs)."""
 
     def __init__(self, device: int = 0, conv_kernel: int = 5):
         if not torch.cuda.is_available():

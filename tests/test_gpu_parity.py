@@ -13,9 +13,9 @@ from helpers import conditioning, load_golden, rmsd
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,4,5").split(",") if k]
+KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,4,5,6").split(",") if k]
 # fp32 score tolerance: |cuda - oracle_fp32| <= RTOL * max|oracle| (fp32 oracle itself is ~2e-6 from fp64)
-RTOL = {0: 2e-4, 1: 2e-4, 2: 5e-2, 3: 2e-4, 4: 2e-4, 5: 2e-4}
+RTOL = {0: 2e-4, 1: 2e-4, 2: 5e-2, 3: 2e-4, 4: 2e-4, 5: 2e-4, 6: 2e-4}
 
 
 @pytest.fixture(scope="module")
@@ -207,3 +207,14 @@ def test_fp16_mode_is_robust_to_weight_and_activation_scale(sd, w1_scale, w2_sca
     for k, o, r in zip(("tr", "rot", "tor", "sc"), out, ref):
         assert torch.isfinite(o).all(), k
         assert (o.double() - r).abs().max().item() <= 2e-4 * max(r.abs().max().item(), 1e-6), k
+
+
+def test_pair_kernel_bit_identical_to_single_cta(sd):
+    """Mode 6 (cta_group::2 CTA pairs) performs the same MMAs in the same order as mode 5: identical bits,
+    including odd tile counts (the peer CTA recomputes the last tile and stores nothing)."""
+    e5, e6 = make_engine(5, sd), make_engine(6, sd)
+    for wl, seed in ((synth.WORKLOADS["tiny"], 3), (dict(n_complex=1, n_poses=3, n_res=36, n_lig=30), 5)):
+        b = synth.make_batch(**wl, seed=seed)
+        c = conditioning(b)
+        for a, r in zip(run_score(e6, b, c), run_score(e5, b, c)):
+            assert torch.equal(a, r)

@@ -454,10 +454,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           for (int ka = 0; ka < KATOMS; ++ka) {
             tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
             if (tc::elect_one()) {
+              if (L.dbg & 32) tc::mbar_arrive(&b_full[st.idx]);   // timing experiment: no weight streaming
+              else {
               tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
               uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
               tc::tma_load_2d(dst, mh, ka * 64, row0, &b_full[st.idx]);
               tc::tma_load_2d(dst + B_PART, ml, ka * 64, row0, &b_full[st.idx]);
+              }
             }
             __syncwarp();
             tc::advance(st, NST);
@@ -689,7 +692,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (pa.Wd == 48) {
+          if (L.dbg & 16) {                            // timing experiment: no fold
+          } else if (pa.Wd == 48) {
             for (int uu = 0; uu < nu; ++uu) {
               float v[48];
               tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);

@@ -76,6 +76,9 @@ int main() {
   for (int grid : {1, 148}) {
     run<0>("TS f16  (A in TMEM)", 144, 2000, 36, grid);
     run<0>("TS f16  (A in TMEM)", 96, 2000, 36, grid);
+    run<0>("TS f16  (A in TMEM)", 128, 2000, 36, grid);
+    run<0>("TS f16  (A in TMEM)", 160, 2000, 36, grid);
+    run<0>("TS f16  (A in TMEM)", 192, 2000, 36, grid);
     run<0>("TS f16  (A in TMEM)", 256, 1000, 36, grid);
     run<1>("SS f16  (A in smem)", 144, 2000, 36, grid);
     run<1>("SS f16  (A in smem)", 256, 1000, 36, grid);

@@ -1,82 +1,32 @@
-// MODE 7: the fused tensor-product convolution with a MIXED-FORMAT error compensation (fp16 main product + two e4m3
-// cross terms).  The shipped fp32-grade scheme (mode 5) computes a.b = ah.bh + ah.bl + al.bh with three fp16 MMAs per K step.
-// The two cross terms are 2^-12 of the main term, so they only need ~4 significant bits to keep the total error near
-// 2^-16: here they run as tcgen05 kind::f8f6f4 MMAs (e4m3, K = 32 per instruction, twice the fp16 rate):
-//
-//   D = fp16(ah) x fp16(bh)  +  e4m3(ah 2^-4) x e4m3(bl 2^4)  +  e4m3(al 2^8) x e4m3(bh 2^-8)        (fp32 accumulation in TMEM)
-//
-// 20 instead of 30 MMA issue slots per 144-column unit (2/3 of the tensor-pipe time and energy); weight streaming is
-// unchanged (2 + 1 + 1 bytes per element).  Measured against the reference fixtures (tools/precision_study.py emulates it
-// on the CPU oracle): per-step scores within 8e-5 relative, 20-step trajectory within 2e-4 A RMSD - inside the 1e-3 A /
-// 2e-4 bars, but ~50x less accurate than mode 5, hence opt-in.  Everything else (tiling, warp roles, per-row power-of-two
-// scaling, fold) is the mode-5 kernel of conv_fused.cuh.
+// MODE 8: mode 7 (fp16 main product + two e4m3 cross-term MMAs, conv_fused8.cuh) on CTA pairs (tcgen05 cta_group::2,
+// conv_fused2.cuh).  With only 20 MMA slots per 144-column unit the single-CTA kernel is bound by the L2 -> shared-memory
+// weight streaming (ncu: 11.4 TB/s, the chip's L2 cap, tensor pipe 59 % active); splitting the B operand across the two
+// SMs of a pair halves that traffic and doubles the ring depth (6 stages of 18 KB per CTA).
 #pragma once
-#include <cuda_fp8.h>
-#include "conv_fused.cuh"
-
-struct Fused8Maps { CUtensorMap w2[4], w2_q8h[4], w2_q8l[4], w1[4], w1_q8h[4], w1_q8l[4]; };
+#include "conv_fused2.cuh"
+#include "conv_fused8.cuh"
 
 namespace tc {
-// K-major SWIZZLE_64B shared-memory matrix descriptor (rows of 64 bytes, 8-row groups 512 B apart)
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                         // SWIZZLE_64B
-  return d;
-}
-// e4m3 x e4m3 -> fp32: same instruction-descriptor encoding as fp16 x fp16 (format code 0), other instruction kind
-__device__ __forceinline__ void mma_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void mma_f8_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t addr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-// 64 scaled fp32 values -> 32 columns of fp16 hi pairs, 16 columns of e4m3(hi 2^-4) quads, 16 columns of e4m3(lo 2^8) quads
-// (element k of a row lives in byte k % 4 of column k / 4, like element k in half k % 2 of column k / 2 for fp16)
-__device__ __forceinline__ void pack_store_f8x(uint32_t addr16, uint32_t addr8h, uint32_t addr8l, const float* v) {
-  float p16[32], p8h[16], p8l[16];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const __half h0 = __float2half_rn(v[2 * c]), h1 = __float2half_rn(v[2 * c + 1]);
-    const float f0 = __half2float(h0), f1 = __half2float(h1);
-    p16[c] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
-    const uint32_t qh = __nv_cvt_float2_to_fp8x2(make_float2(f0 * 0.0625f, f1 * 0.0625f), __NV_SATFINITE, __NV_E4M3);
-    const uint32_t ql = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * c] - f0) * 256.0f, (v[2 * c + 1] - f1) * 256.0f), __NV_SATFINITE, __NV_E4M3);
-    if (c & 1) {
-      p8h[c >> 1] = __uint_as_float(__float_as_uint(p8h[c >> 1]) | (qh << 16));
-      p8l[c >> 1] = __uint_as_float(__float_as_uint(p8l[c >> 1]) | (ql << 16));
-    } else {
-      p8h[c >> 1] = __uint_as_float(qh);
-      p8l[c >> 1] = __uint_as_float(ql);
-    }
-  }
-  tmem_st32(addr16, p16);
-  tmem_st16(addr8h, p8h);
-  tmem_st16(addr8l, p8l);
 }
 }  // namespace tc
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
-  constexpr int BN = F16_BN, NST = F16_NST;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_conv_fused8x2(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
+  constexpr int BN = F16_BN, NST = F2_NST, HB = F2_HB;
   constexpr int KATOMS = 3;                      // K = 192 halves = 3 swizzle atoms of 64 fp16
   constexpr int A8H = 96, A8L = 144;             // tensor-memory columns: fp16 hi [0,96), e4m3(hi) [96,144), e4m3(lo) [144,192)
-  constexpr int D0 = 192;                        // accumulator buffers at columns [192,288) and [288,384)
-  constexpr uint32_t B16 = BN * 128, B8 = BN * 64;   // bytes of one K-atom: fp16 hi (SW128), each e4m3 term (SW64)
+  constexpr int D0 = 192;                        // accumulator buffers at columns [192,336) and [336,480)
+  constexpr uint32_t B16 = HB * 128, B8 = HB * 64;   // bytes of one half-unit K-atom: fp16 hi (SW128), each e4m3 term (SW64)
   constexpr uint32_t STAGE = B16 + 2 * B8;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sB = base;                                              // [NST][fp16 hi | e4m3(hi) | e4m3(lo)]
+  uint8_t* sB = base;                                              // [NST][2][72 x 128 B]
   float* x1s = reinterpret_cast<float*>(sB + (size_t)NST * STAGE);   // [128][169] per-edge scratch rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(x1s + 128 * F_X1S);
   uint64_t* x_full = bars;            uint64_t* h_full = bars + 1;  uint64_t* a_empty = bars + 2;
@@ -85,23 +35,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int cid = blockIdx.x >> 1, nclus = gridDim.x >> 1;
   if (threadIdx.x == 0) {
-    tc::mbar_init(x_full, 128); tc::mbar_init(h_full, 128); tc::mbar_init(a_empty, 1);
+    tc::mbar_init(x_full, 8); tc::mbar_init(h_full, 8); tc::mbar_init(a_empty, 1);
     for (int s = 0; s < NST; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc::fence_before();
   __syncthreads();
+  tc::cluster_sync_all();                        // barriers of both CTAs initialised before any remote arrive / multicast
   tc::fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (both CTAs: own 72 rows)
     if (lane == 0)
       for (int ci = 0; ci < L.n; ++ci) {
         tc::prefetch_tmap(&maps.w2[ci]); tc::prefetch_tmap(&maps.w2_q8h[ci]); tc::prefetch_tmap(&maps.w2_q8l[ci]);
@@ -109,30 +62,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
       }
     __syncwarp();
     tc::Phase st;
-    int tiles_before = 0;
+    int pairs_before = 0;
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
       const DevPlan& P = c_plans[C.plan];
       const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
-      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
-      tiles_before += ntile;
-      for (int tile = first; tile < ntile; tile += gridDim.x) {
+      const int npair = (ntile + 1) >> 1;
+      int first = (int)((cid + nclus - (pairs_before % nclus)) % nclus);
+      pairs_before += npair;
+      for (int pair = first; pair < npair; pair += nclus) {
         for (int unit = -1; unit < P.n_chunks; ++unit) {
           const CUtensorMap* mh = unit < 0 ? &maps.w1[ci] : &maps.w2[ci];
           const CUtensorMap* m8h = unit < 0 ? &maps.w1_q8h[ci] : &maps.w2_q8h[ci];
           const CUtensorMap* m8l = unit < 0 ? &maps.w1_q8l[ci] : &maps.w2_q8l[ci];
-          const int row0 = unit < 0 ? 0 : P.chunk_col[unit];
+          const int row0 = (unit < 0 ? 0 : P.chunk_col[unit]) + (int)rank * HB;
           for (int ka = 0; ka < KATOMS; ++ka) {
-            tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
+            tc::mbar_wait_cluster(&b_empty[st.idx], st.par ^ 1);
             if (tc::elect_one()) {
-              if (L.dbg & 32) tc::mbar_arrive(&b_full[st.idx]);   // timing experiment: no weight streaming
-              else {
-              tc::mbar_expect_tx(&b_full[st.idx], STAGE);
+              const uint32_t full0 = tc::map_to_cta(&b_full[st.idx], 0);
+              if (rank == 0) tc::mbar_expect_tx(&b_full[st.idx], 2 * STAGE);
               uint8_t* dst = sB + (size_t)st.idx * STAGE;
-              tc::tma_load_2d(dst, mh, ka * 64, row0, &b_full[st.idx]);
-              tc::tma_load_2d(dst + B16, m8h, ka * 64, row0, &b_full[st.idx]);
-              tc::tma_load_2d(dst + B16 + B8, m8l, ka * 64, row0, &b_full[st.idx]);
-              }
+              tc::tma_load_2d_pair(dst, mh, ka * 64, row0, full0);
+              tc::tma_load_2d_pair(dst + B16, m8h, ka * 64, row0, full0);
+              tc::tma_load_2d_pair(dst + B16 + B8, m8l, ka * 64, row0, full0);
             }
             __syncwarp();
             tc::advance(st, NST);
@@ -140,93 +92,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================================================================= MMA issuer
-    // Every unit consumes exactly KATOMS == NST ring stages, so stage index == K-atom index and the
-    // shared-memory descriptors are loop invariant: all per-stage setup is hoisted out of the issue loop.
-    static_assert(F16_NST == 3, "stage == k-atom mapping");
-    tc::Phase db;
-    uint32_t xpar = 0, hpar = 0, bpar = 0;
-    uint64_t dhs[KATOMS], d8h[KATOMS], d8l[KATOMS];
-#pragma unroll
-    for (int ka = 0; ka < KATOMS; ++ka) {
-      const uint32_t b_hi = tc::smem_u32(sB + (size_t)ka * STAGE);
-      dhs[ka] = tc::make_desc(b_hi); d8h[ka] = tc::make_desc_sw64(b_hi + B16); d8l[ka] = tc::make_desc_sw64(b_hi + B16 + B8);
+    for (int i = 0; i < NST; ++i) {              // tail: every stage released, i.e. no multicast arrive still in flight
+      tc::mbar_wait_cluster(&b_empty[st.idx], st.par ^ 1);
+      tc::advance(st, NST);
     }
-    int tiles_before = 0;
+  } else if (warp == 1 && rank == 0) {
+    // ======================================================================= MMA issuer (leader CTA only)
+    // Every unit consumes KATOMS = 3 ring stages and NST = 6, so stage = (unit parity) * 3 + k-atom: descriptors hoisted.
+    tc::Phase db;
+    uint32_t xpar = 0, hpar = 0, bpar0 = 0, bpar1 = 0;
+    uint64_t dhs[NST], d8hs[NST], d8ls[NST];
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      const uint32_t b_hi = tc::smem_u32(sB + (size_t)s * STAGE);
+      dhs[s] = tc::make_desc(b_hi); d8hs[s] = tc::make_desc_sw64(b_hi + B16); d8ls[s] = tc::make_desc_sw64(b_hi + B16 + B8);
+    }
+    const uint32_t idesc = tc::make_idesc_f16(256, BN);
+    int pairs_before = 0;
+    uint32_t useq = 0;                                  // running unit counter -> ring half
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
       const DevPlan& P = c_plans[C.plan];
       const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
-      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
-      tiles_before += ntile;
-      for (int tile = first; tile < ntile; tile += gridDim.x) {
-        tc::mbar_wait(x_full, xpar);
+      const int npair = (ntile + 1) >> 1;
+      int first = (int)((cid + nclus - (pairs_before % nclus)) % nclus);
+      pairs_before += npair;
+      for (int pair = first; pair < npair; pair += nclus) {
+        tc::mbar_wait_cluster(x_full, xpar);
         xpar ^= 1;
         tc::fence_after();
-        for (int unit = -1; unit < P.n_chunks; ++unit) {
+        for (int unit = -1; unit < P.n_chunks; ++unit, ++useq) {
           if (unit == 0) {                              // H1 must be in tensor memory before the W2 units
-            tc::mbar_wait(h_full, hpar);
+            tc::mbar_wait_cluster(h_full, hpar);
             hpar ^= 1;
             tc::fence_after();
           }
-          const int N = unit < 0 ? 144 : P.chunk_n[unit];
-          const uint32_t idesc = tc::make_idesc_f16(128, N);
+          const uint32_t half = useq & 1;
           const uint32_t d_tmem = tmem_base + (uint32_t)(D0 + db.idx * BN);
           const bool last_unit = (unit + 1 == P.n_chunks);
-          tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
+          tc::mbar_wait_cluster(&d_empty[db.idx], db.par ^ 1);
           tc::fence_after();
 #pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
-            tc::mbar_wait(&b_full[ka], bpar);
+            const int s = half ? KATOMS + ka : ka;
+            tc::mbar_wait_cluster(&b_full[s], half ? bpar1 : bpar0);
             tc::fence_after();
             if (tc::elect_one()) {
+              const uint64_t dh = half ? dhs[KATOMS + ka] : dhs[ka];
+              const uint64_t d8h = half ? d8hs[KATOMS + ka] : d8hs[ka], d8l = half ? d8ls[KATOMS + ka] : d8ls[ka];
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {                  // e4m3 cross terms, K = 32 per MMA: hi x lo' and lo' x hi
+              for (int j = 0; j < 2; ++j) {                  // e4m3 cross terms, K = 32 per MMA: lo' x hi and hi x lo'
                 if (ka == KATOMS - 1 && j >= 1) continue;    // K = 145 real columns: bytes 160..191 are zero padding
                 const uint32_t a8 = tmem_base + (uint32_t)(ka * 16 + j * 8);
-                tc::mma_f8_ts(d_tmem, a8 + A8L, d8h[ka] + (uint64_t)(j * 2), idesc, (ka | j) ? 1u : 0u);
-                tc::mma_f8_ts(d_tmem, a8 + A8H, d8l[ka] + (uint64_t)(j * 2), idesc, 1u);
+                tc::mma_f8_ts_pair(d_tmem, a8 + A8L, d8h + (uint64_t)(j * 2), idesc, (ka | j) ? 1u : 0u);
+                tc::mma_f8_ts_pair(d_tmem, a8 + A8H, d8l + (uint64_t)(j * 2), idesc, 1u);
               }
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {               // fp16 main term, K = 16 per MMA
                 if (ka == KATOMS - 1 && k8 >= 2) continue;
-                tc::mma_f16_ts(d_tmem, tmem_base + (uint32_t)(ka * 32 + k8 * 8), dhs[ka] + (uint64_t)(k8 * 2), idesc, 1u);
+                tc::mma_f16_ts_pair(d_tmem, tmem_base + (uint32_t)(ka * 32 + k8 * 8), dh + (uint64_t)(k8 * 2), idesc, 1u);
               }
-              tc::mma_commit(&b_empty[ka]);
+              tc::mma_commit_pair(&b_empty[s]);
               if (ka == KATOMS - 1) {
-                tc::mma_commit(&d_full[db.idx]);
-                if (last_unit) tc::mma_commit(a_empty);
+                tc::mma_commit_pair(&d_full[db.idx]);
+                if (last_unit) tc::mma_commit_pair(a_empty);
               }
             }
             __syncwarp();
           }
-          bpar ^= 1;
+          if (half) bpar1 ^= 1; else bpar0 ^= 1;
           tc::advance(db, 2);
         }
       }
     }
   } else if (warp >= 4) {
-    // ================================================== gather / H1 / epilogue warps (thread = edge)
+    // ================================================== gather / H1 / epilogue warps (thread = edge), both CTAs
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     float* xrow = x1s + row * F_X1S;
+    const uint32_t x_full0 = tc::map_to_cta(x_full, 0), h_full0 = tc::map_to_cta(h_full, 0);
+    const uint32_t d_empty0[2] = {tc::map_to_cta(&d_empty[0], 0), tc::map_to_cta(&d_empty[1], 0)};
     tc::Phase db;
     uint32_t apar = 0;
-    int tiles_before = 0;
+    int pairs_before = 0;
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
       const DevPlan& P = c_plans[C.plan];
       const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
-      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
-      tiles_before += ntile;
-      for (int tile = first; tile < ntile; tile += gridDim.x) {
+      const int npair = (ntile + 1) >> 1;
+      int first = (int)((cid + nclus - (pairs_before % nclus)) % nclus);
+      pairs_before += npair;
+      for (int pair = first; pair < npair; pair += nclus) {
+        int tile = 2 * pair + (int)rank;
+        const bool live = tile < ntile;                 // odd tile count: the peer recomputes the last tile, stores nothing
+        if (!live) tile = ntile - 1;
         const int e = tile * TILE_E + row;
         const int s = C.es[e], d = C.ed[e];
         float sx = 1.0f, shh = 1.0f;
         // ---- 1. xin -> tensor memory
-        tc::mbar_wait(a_empty, apar ^ 1);
+        tc::mbar_wait_cluster(a_empty, apar ^ 1);
         apar ^= 1;
         tc::fence_after();
         {
@@ -238,7 +203,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
             pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
             pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
           }
-          {
           float4 xf[36];                                 // the whole edge-input row in flight at once
 #pragma unroll
           for (int k4 = 0; k4 < 12; ++k4) xf[k4] = __ldg(pe + k4);
@@ -269,10 +233,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
             }
             tc::pack_store_f8x(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(A8H + g * 16), lane_base + (uint32_t)(A8L + g * 16), v);
           }
-          }
           tc::tmem_wait_st();
           tc::fence_before();
-          tc::mbar_arrive(x_full);
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive_cluster(x_full0);
         }
         // ---- x1 row -> per-thread scratch, edge harmonics -> registers
         {
@@ -297,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
         // ---- 3. D1 -> relu -> H1 hi/lo -> tensor memory
         {
           tc::Phase p0 = db; tc::advance(db, 2);
-          tc::mbar_wait(&d_full[p0.idx], p0.par);
+          tc::mbar_wait_cluster(&d_full[p0.idx], p0.par);
           tc::fence_after();
           const uint32_t t0 = lane_base + (uint32_t)(D0 + p0.idx * BN);
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
@@ -331,8 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
           tc::tmem_wait_st();
           tc::fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&d_empty[p0.idx]);
-          tc::mbar_arrive(h_full);
+          if (lane == 0) { tc::mbar_arrive_cluster(d_empty0[p0.idx]); tc::mbar_arrive_cluster(h_full0); }
         }
         // ---- 5. W2 units: fold with Z computed on the fly
         float* mrow = C.msg + (size_t)e * HS;
@@ -364,12 +327,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
           }
           const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
           const float* xp = xrow + pa.in1_off + u0 * d1;
-          tc::mbar_wait(&d_full[db.idx], db.par);
+          tc::mbar_wait_cluster(&d_full[db.idx], db.par);
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (L.dbg & 16) {                            // timing experiment: no fold
-          } else if (pa.Wd == 48) {
+          if (pa.Wd == 48) {
             for (int uu = 0; uu < nu; ++uu) {
               float v[48];
               tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
@@ -401,73 +363,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused8(ConvLaunch L, con
           }
           tc::fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&d_empty[db.idx]);
+          if (lane == 0) tc::mbar_arrive_cluster(d_empty0[db.idx]);
           tc::advance(db, 2);
           bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
           if (last) {
             const int nout = (pa.Wd == 48) ? 48 : 36;
 #pragma unroll
             for (int i = 0; i < 48; i += 4) {
-              if (i < nout) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+              if (i < nout && live) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
               o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
             }
           }
         }
       }
     }
+    tc::mbar_wait_cluster(a_empty, apar ^ 1);    // tail: the last tile's release has landed in this CTA
   }
   tc::fence_before();
   __syncthreads();
+  tc::cluster_sync_all();                        // no remote arrive / multicast may target a CTA that already left
   if (warp == 2) {
     tc::fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
-// fp32 [rows][160] (K-major, packed W2p / W1p) scaled by `scale` -> fp16 hi [rows_out][192], e4m3(hi 2^-8) and e4m3(lo 2^4)
-// [rows_out][192] bytes each
-__global__ void k_build_w8(const float* __restrict__ src, int rows, int rows_out, float scale, __half* __restrict__ hi,
-                           uint8_t* __restrict__ q8h, uint8_t* __restrict__ q8l) {
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)rows_out * KH; idx += (size_t)gridDim.x * blockDim.x) {
-    int j = (int)(idx / KH), k = (int)(idx % KH);
-    float v = (j < rows && k < KP) ? src[(size_t)j * KP + k] * scale : 0.0f;
-    __half h = __float2half_rn(v);
-    const float f = __half2float(h);
-    hi[idx] = h;
-    q8h[idx] = (uint8_t)__nv_cvt_float_to_fp8(f * 0.00390625f, __NV_SATFINITE, __NV_E4M3);
-    q8l[idx] = (uint8_t)__nv_cvt_float_to_fp8((v - f) * 16.0f, __NV_SATFINITE, __NV_E4M3);
-  }
+static inline int conv_fused8x2_init() {
+  return cudaFuncSetAttribute(k_conv_fused8x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM) == cudaSuccess ? 0 : 1;
 }
 
-static inline int tc_make_map8(CUtensorMap* m, const void* ptr, uint64_t rows, uint32_t box_rows) {
-  cuuint64_t gdim[2] = {KH, rows};
-  cuuint64_t gstr[1] = {KH};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 1;
-}
-
-static inline int conv_fused8_init() {
-  return cudaFuncSetAttribute(k_conv_fused8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F16_SMEM) == cudaSuccess ? 0 : 1;
-}
-
-// X.W?hi = fp16 hi arrays; X.W?lo = the e4m3 block of the same conv: [rows][192] bytes e4m3(hi) followed by [rows][192] bytes e4m3(lo)
-static inline int launch_conv_fused8(const ConvLaunch& L, const Fused16Extra& X, int grid, cudaStream_t st) {
+static inline int launch_conv_fused8x2(const ConvLaunch& L, const Fused16Extra& X, int grid, cudaStream_t st) {
   if (!g_encode) return 1;
   Fused8Maps maps;
   memset(&maps, 0, sizeof maps);
   for (int i = 0; i < L.n; ++i) {
     const uint8_t* q2 = reinterpret_cast<const uint8_t*>(X.W2lo[i]);
     const uint8_t* q1 = reinterpret_cast<const uint8_t*>(X.W1lo[i]);
-    if (tc_make_map16(&maps.w2[i], X.W2hi[i], X.w2_rows[i], F16_BN)) return 2;
-    if (tc_make_map8(&maps.w2_q8h[i], q2, X.w2_rows[i], F16_BN)) return 3;
-    if (tc_make_map8(&maps.w2_q8l[i], q2 + (size_t)X.w2_rows[i] * KH, X.w2_rows[i], F16_BN)) return 3;
-    if (tc_make_map16(&maps.w1[i], X.W1hi[i], 192, F16_BN)) return 4;
-    if (tc_make_map8(&maps.w1_q8h[i], q1, 192, F16_BN)) return 5;
-    if (tc_make_map8(&maps.w1_q8l[i], q1 + (size_t)192 * KH, 192, F16_BN)) return 5;
+    if (tc_make_map16(&maps.w2[i], X.W2hi[i], X.w2_rows[i], F2_HB)) return 2;
+    if (tc_make_map8(&maps.w2_q8h[i], q2, X.w2_rows[i], F2_HB)) return 3;
+    if (tc_make_map8(&maps.w2_q8l[i], q2 + (size_t)X.w2_rows[i] * KH, X.w2_rows[i], F2_HB)) return 3;
+    if (tc_make_map16(&maps.w1[i], X.W1hi[i], 192, F2_HB)) return 4;
+    if (tc_make_map8(&maps.w1_q8h[i], q1, 192, F2_HB)) return 5;
+    if (tc_make_map8(&maps.w1_q8l[i], q1 + (size_t)192 * KH, 192, F2_HB)) return 5;
   }
-  k_conv_fused8<<<grid, TC_THREADS, F16_SMEM, st>>>(L, maps);
+  k_conv_fused8x2<<<grid & ~1, TC_THREADS, F2_SMEM, st>>>(L, maps);
   return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }

@@ -3,9 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_fp16.h>
-#include "conv_fused.cuh"
+#include "conv_fused8.cuh"
 
-template <int MODE>   // 0: TS f16, 1: SS f16 (A from smem), 2: TS tf32
+template <int MODE>   // 0: TS f16, 1: SS f16 (A from smem), 2: TS tf32, 3: TS e4m3 (kind::f8f6f4, K = 32), 4: mode-7 mix (2 e4m3 : 1 f16 ... per unit 10 + 10)
 __global__ void __launch_bounds__(128, 1) k_bench(int N, int units, int mmas_per_unit, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(128, 1) k_bench(int N, int units, int mmas_per
         for (int m = 0; m < mmas_per_unit; ++m) {
           const uint64_t b = bd + (uint64_t)((m & 3) * 2) + (uint64_t)(((m >> 2) % 3) * (2 * 144 * 128 / 16));
           if (MODE == 0) tc::mma_f16_ts(d, tb + (m & 3) * 8, b, idesc, m ? 1u : 0u);
+          else if (MODE == 3) tc::mma_f8_ts(d, tb + (m & 3) * 8, b, idesc, m ? 1u : 0u);
+          else if (MODE == 4) { if (m & 1) tc::mma_f8_ts(d, tb + (m & 3) * 8, b, idesc, 1u); else tc::mma_f16_ts(d, tb + (m & 3) * 8, b, idesc, m ? 1u : 0u); }
           else if (MODE == 2) tc::mma_tf32_ts(d, tb + (m & 3) * 8, b, idesc, m ? 1u : 0u);
           else {
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -75,13 +77,10 @@ template <int MODE> void run(const char* name, int N, int units, int mpu, int gr
 int main() {
   for (int grid : {1, 148}) {
     run<0>("TS f16  (A in TMEM)", 144, 2000, 36, grid);
-    run<0>("TS f16  (A in TMEM)", 96, 2000, 36, grid);
     run<0>("TS f16  (A in TMEM)", 128, 2000, 36, grid);
-    run<0>("TS f16  (A in TMEM)", 160, 2000, 36, grid);
-    run<0>("TS f16  (A in TMEM)", 192, 2000, 36, grid);
-    run<0>("TS f16  (A in TMEM)", 256, 1000, 36, grid);
-    run<1>("SS f16  (A in smem)", 144, 2000, 36, grid);
-    run<1>("SS f16  (A in smem)", 256, 1000, 36, grid);
+    run<3>("TS e4m3 (A in TMEM, K=32)", 144, 2000, 36, grid);
+    run<3>("TS e4m3 (A in TMEM, K=32)", 128, 2000, 36, grid);
+    run<4>("TS f16/e4m3 alternating", 144, 2000, 36, grid);
     run<2>("TS tf32 (A in TMEM)", 96, 2000, 60, grid);
   }
   return 0;

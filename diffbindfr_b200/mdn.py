@@ -95,7 +95,7 @@ def pack_encoder_weights(sd: Dict[str, torch.Tensor]) -> Tuple[np.ndarray, np.nd
 
 def _csr(target: torch.Tensor, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
     perm = torch.argsort(target, stable=True)
-    ptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(target, minlength=n).cumsum(0)])
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long, device=target.device), torch.bincount(target, minlength=n).cumsum(0)])
     return perm.int(), ptr.int()
 
 
@@ -122,10 +122,10 @@ class MDNScorer:
         dev = self._dev()
         f = lambda t: t.float().contiguous().to(dev)
         i = lambda t: t.int().contiguous().to(dev)
-        m = data["lig_cov_edge_mask"].bool().cpu()
-        lei = data["lig_edge_index"].cpu()[:, m]
-        les = data["lig_edge_s"].cpu()[m]
-        pei = data["pro_edge_index"].cpu()
+        m = data["lig_cov_edge_mask"].bool()
+        lei = data["lig_edge_index"][:, m.to(data["lig_edge_index"].device)]
+        les = data["lig_edge_s"][m.to(data["lig_edge_s"].device)]
+        pei = data["pro_edge_index"]
         N_r, N_l = data["pro_node_s"].shape[0], data["lig_node_s"].shape[0]
         pperm, pptr = _csr(pei[1], N_r)
         lperm, lptr = _csr(lei[1], N_l)
@@ -142,7 +142,7 @@ class MDNScorer:
     def scoring(self, lig_s, lig_pos, lig_batch, pro_s, xyz_full, pro_batch, dist_threhold: float = 5.0) -> torch.Tensor:
         dev = self._dev()
         B = int(lig_batch.max()) + 1
-        ptr = lambda b: torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(b.cpu(), minlength=B).cumsum(0)]).int().to(dev)
+        ptr = lambda b: torch.cat([torch.zeros(1, dtype=torch.long, device=b.device), torch.bincount(b, minlength=B).cumsum(0)]).int().to(dev)
         t = [lig_s.float().contiguous().to(dev), lig_pos.float().contiguous().to(dev), ptr(lig_batch),
              pro_s.float().contiguous().to(dev), xyz_full.float().contiguous().to(dev), ptr(pro_batch)]
         mb = CMdnBatch(B, t[0].shape[0], t[3].shape[0], *[x.data_ptr() for x in t])

@@ -23,54 +23,65 @@ def batches(indices: Sequence[int], batch_size: int) -> List[List[int]]:
     return [list(indices[i:i + batch_size]) for i in range(0, len(indices), batch_size)]
 
 
+HDR = 4   # record header: sample id (or -1), n_l, n_r, MDN score (NaN when the sample was not scored)
+
+
 def pack_records(ids: Sequence[int], ligs: Sequence[torch.Tensor], a14s: Sequence[torch.Tensor], max_nl: int,
-                 max_nr: int, n_slots: int, device=None) -> torch.Tensor:
-    """[n_slots, 3 + max_nl*3 + max_nr*42] float32: (sample id or -1, n_l, n_r, lig xyz, atom14 xyz)."""
-    stride = 3 + max_nl * 3 + max_nr * 42
+                 max_nr: int, n_slots: int, device=None, scores: Optional[Sequence[float]] = None) -> torch.Tensor:
+    """[n_slots, 4 + max_nl*3 + max_nr*42] float32: (sample id or -1, n_l, n_r, MDN score, lig xyz, atom14 xyz)."""
+    stride = HDR + max_nl * 3 + max_nr * 42
     rec = torch.zeros(n_slots, stride, dtype=torch.float32, device=device)
     rec[:, 0] = -1
+    rec[:, 3] = float("nan")
     for k, (i, l, a) in enumerate(zip(ids, ligs, a14s)):
         rec[k, 0], rec[k, 1], rec[k, 2] = float(i), float(l.shape[0]), float(a.shape[0])
-        rec[k, 3:3 + l.numel()] = l.reshape(-1).to(rec)
-        rec[k, 3 + max_nl * 3:3 + max_nl * 3 + a.numel()] = a.reshape(-1).to(rec)
+        if scores is not None:
+            rec[k, 3] = float(scores[k])
+        rec[k, HDR:HDR + l.numel()] = l.reshape(-1).to(rec)
+        rec[k, HDR + max_nl * 3:HDR + max_nl * 3 + a.numel()] = a.reshape(-1).to(rec)
     return rec
 
 
-def unpack_records(rec: torch.Tensor, max_nl: int) -> Dict[int, Tuple[torch.Tensor, torch.Tensor]]:
+def unpack_records(rec: torch.Tensor, max_nl: int, with_scores: bool = False):
     out = {}
     for r in rec.reshape(-1, rec.shape[-1]):
         i = int(r[0].item())
         if i < 0:
             continue
         nl, nr = int(r[1].item()), int(r[2].item())
-        out[i] = (r[3:3 + nl * 3].reshape(nl, 3).clone(), r[3 + max_nl * 3:3 + max_nl * 3 + nr * 42].reshape(nr, 14, 3).clone())
+        lig = r[HDR:HDR + nl * 3].reshape(nl, 3).clone()
+        a14 = r[HDR + max_nl * 3:HDR + max_nl * 3 + nr * 42].reshape(nr, 14, 3).clone()
+        out[i] = (lig, a14, float(r[3].item())) if with_scores else (lig, a14)
     return out
 
 
-def gather_poses(ids, ligs, a14s, n_samples: int, max_nl: int, max_nr: int, group=None, device=None):
-    """One collective: every rank ends with {sample id: (lig (n_l,3), atom14 (n_r,14,3))} for all samples."""
+def gather_poses(ids, ligs, a14s, n_samples: int, max_nl: int, max_nr: int, group=None, device=None, scores=None):
+    """One collective: every rank ends with {sample id: (lig (n_l,3), atom14 (n_r,14,3)[, MDN score])} for all samples."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n_slots = (n_samples + world - 1) // world
-    rec = pack_records(ids, ligs, a14s, max_nl, max_nr, n_slots, device)
+    rec = pack_records(ids, ligs, a14s, max_nl, max_nr, n_slots, device, scores)
     if world == 1:
-        return unpack_records(rec, max_nl)
+        return unpack_records(rec, max_nl, scores is not None)
     out = [torch.empty_like(rec) for _ in range(world)]
     dist.all_gather(out, rec, group=group)
-    return unpack_records(torch.stack(out).cpu(), max_nl)
+    return unpack_records(torch.stack(out).cpu(), max_nl, scores is not None)
 
 
 def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], List[Tuple[torch.Tensor, torch.Tensor]]],
                 batch_size: int, collate=None, group=None, device=None):
     """Deal ``samples`` to ranks, run ``run_batch`` on local batches, gather all final poses.
-    ``run_batch(list_of_samples)`` returns [(lig (n_l,3), atom14 (n_r,14,3))] per sample."""
+    ``run_batch(list_of_samples)`` returns [(lig (n_l,3), atom14 (n_r,14,3))] per sample, or 3-tuples with the sample's
+    MDN score appended (the scorer runs on the rank that sampled the pose; the score travels in the same record)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     mine = shard_indices(len(samples), rank, world)
-    ids, ligs, a14s = [], [], []
+    ids, ligs, a14s, scores = [], [], [], []
     for chunk in batches(mine, batch_size):
         res = run_batch([samples[i] for i in chunk])
-        for i, (l, a) in zip(chunk, res):
-            ids.append(i); ligs.append(l); a14s.append(a)
+        for i, r in zip(chunk, res):
+            ids.append(i); ligs.append(r[0]); a14s.append(r[1])
+            if len(r) > 2:
+                scores.append(float(r[2]))
     max_nl = max(int(s["lig_pos"].shape[0]) for s in samples)
     max_nr = max(int(s["sequence"].shape[0]) for s in samples)
-    return gather_poses(ids, ligs, a14s, len(samples), max_nl, max_nr, group, device)
+    return gather_poses(ids, ligs, a14s, len(samples), max_nl, max_nr, group, device, scores if len(scores) == len(ids) and ids else None)

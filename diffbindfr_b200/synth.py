@@ -343,3 +343,31 @@ def make_mdn_complexes(seed: int = 0, n_lig=(12, 30, 7), n_res=(20, 36, 11), top
         r_off += nr; l_off += nl
     cat1 = ("pro_edge_index", "lig_edge_index")
     return {k: torch.cat(v, 1 if k in cat1 else 0) for k, v in parts.items()}
+
+
+def make_mdn_static(batch: Dict[str, object], poses_per_complex: int, seed: int = 0):
+    """Pose-independent MDN scorer inputs per complex of a ``make_batch`` batch (pose-major per complex): what the dataset
+    featuriser would provide once per (pocket, ligand) pair - residue types, atom14 mask, backbone dihedral sin/cos (synthetic
+    angles), ligand atom (89) / covalent bond (20) features and the covalent edge list (both directions)."""
+    g = torch.Generator().manual_seed(seed)
+    lb = torch.as_tensor(batch["lig_node_batch"])
+    amask = torch.as_tensor(batch["atom14_mask"]).bool()
+    b14 = torch.zeros(amask.shape, dtype=torch.long)
+    b14[amask] = torch.as_tensor(batch["rec_atm_pos_batch"])
+    res_graph = b14.amax(-1)
+    ei = torch.as_tensor(batch["lig_edge_index"]).long()
+    out = []
+    for c in range(int(batch["num_graphs"]) // poses_per_complex):
+        g0 = c * poses_per_complex
+        rs = res_graph == g0
+        n = int(rs.sum())
+        ang = (torch.rand(n, 3, generator=g) * 2 - 1) * math.pi
+        atoms = torch.nonzero(lb == g0).flatten()
+        a0, nl = int(atoms[0]), atoms.numel()
+        em = (ei[0] >= a0) & (ei[0] < a0 + nl)
+        cov = ei[:, em] - a0
+        out.append(dict(seq=torch.as_tensor(batch["sequence"])[rs].long(), atom14_mask=amask[rs], 
+                        bb_dihedral_sincos=torch.stack([ang.sin(), ang.cos()], -1).reshape(n, 6),
+                        lig_node_s=(torch.rand(nl, 89, generator=g) < 0.15).float(),
+                        lig_edge_s=(torch.rand(cov.shape[1], 20, generator=g) < 0.25).float(), lig_edge_index=cov))
+    return out

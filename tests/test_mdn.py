@@ -127,3 +127,51 @@ def test_cuda_encoders_require_weights():
     sc = MDNScorer(Engine(0))
     with pytest.raises(RuntimeError):
         sc.encoding(synth.make_mdn_complexes(seed=1))
+
+
+def test_batched_featuriser_equals_per_pose_featuriser():
+    """protein_features_batched (P poses of one pocket at once) == protein_features pose by pose, incl. edge order."""
+    import numpy as np
+    from diffbindfr_b200 import mdn_features
+    rng = np.random.default_rng(0)
+    pk = synth.make_pocket(rng, 14)
+    base = torch.from_numpy(pk["atom14_position"]).float()
+    mask = torch.from_numpy(pk["atom14_mask"].astype(np.float32))
+    poses = torch.stack([base, base + 0.3 * torch.randn(base.shape) * mask[..., None] * (torch.arange(14) >= 5)[None, :, None]])
+    dih = torch.randn(14, 6)
+    fb = mdn_features.protein_features_batched(poses, mask, dih, topk=5)
+    for p in range(2):
+        f1 = mdn_features.protein_features(poses[p], mask, dih, topk=5)
+        E = f1["edge_index"].shape[1]
+        assert torch.equal(fb["edge_index"][:, p * E:(p + 1) * E] - p * 14, f1["edge_index"])
+        assert torch.allclose(fb["edge_s"][p * E:(p + 1) * E], f1["edge_s"], atol=1e-6)
+        assert torch.allclose(fb["edge_v"][p * E:(p + 1) * E], f1["edge_v"], atol=1e-6)
+        assert torch.allclose(fb["node_s"][p * 14:(p + 1) * 14], f1["node_s"], atol=1e-6)
+        assert torch.allclose(fb["node_v"][p * 14:(p + 1) * 14], f1["node_v"], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_sampler_to_mdn_pipeline_matches_oracle_scorer():
+    """configs[2] path at test size: reverse-SDE sampler -> device featuriser -> MDN scorer; the scores equal the CPU oracle
+    scorer applied to the same final poses (featurised by the same restated function on CPU tensors)."""
+    from diffbindfr_b200 import pipeline, schedule
+    from diffbindfr_b200.engine import Engine
+    from diffbindfr_b200.mdn import MDNScorer
+    from oracle import mdn_encoders as oenc
+    P = 3
+    b = synth.make_batch(n_complex=2, n_poses=P, n_res=12, n_lig=9, seed=5)
+    static = synth.make_mdn_static(b, P, seed=1)
+    eng = Engine(0)
+    eng.load_state_dict(weights.random_state_dict(0))
+    sc = MDNScorer(eng)
+    ksd = weights.random_karmadock_state_dict(0)
+    sc.load_state_dict(ksd)
+    sch = schedule.make_schedule()[:4]
+    B, n_tor, n_sc = b["num_graphs"], int(b["tor_edge_mask"].sum()), int(b["sc_torsion_edge_mask"].sum())
+    noise = torch.randn(4, 6 * B + n_tor + n_sc, generator=torch.Generator().manual_seed(2))
+    lig, a14, scores = pipeline.dock_and_score(eng, sc, b, sch, noise, static, P)
+    torch.cuda.synchronize()
+    x = pipeline.mdn_inputs_from_poses(lig.cpu(), a14.cpu(), b, static, P)
+    ref = oenc.karmadock_forward(ksd, x)
+    assert scores.shape == (B,) and torch.isfinite(scores).all()
+    assert torch.allclose(scores.cpu(), ref, rtol=2e-4, atol=1e-4), (scores.cpu(), ref)

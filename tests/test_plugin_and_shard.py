@@ -89,6 +89,10 @@ def _worker(rank, world, port, q):
     for i, s in enumerate(samples):
         ok &= torch.allclose(got[i][0], torch.from_numpy(s["lig_pos"]) * 2 + 1)
         ok &= torch.allclose(got[i][1], torch.from_numpy(s["atom14_position"]) - 3)
+    # with MDN scores riding in the same records (the job's only collective)
+    got = shard.run_sharded(samples, lambda ch: [(a, b, float(a.sum())) for a, b in run_batch(ch)], batch_size=3)
+    for i, s in enumerate(samples):
+        ok &= abs(got[i][2] - float((torch.from_numpy(s["lig_pos"]) * 2 + 1).sum())) < 1e-3
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -219,3 +219,50 @@ def test_pair_kernel_bit_identical_to_single_cta(sd):
         c = conditioning(b)
         for a, r in zip(run_score(e6, b, c), run_score(e5, b, c)):
             assert torch.equal(a, r)
+
+
+# ---------------------------------------------------------------- BASELINE.json workload shapes
+@pytest.mark.parametrize("name,wl,seed", [
+    ("3dbs_shape", dict(n_complex=1, n_poses=1, n_res=105, n_lig=35), 21),           # configs[0]: 105 residues / ~866 atoms / 35 ligand atoms
+    ("posebusters_ragged", dict(n_complex=3, n_poses=1, n_res=(30, 110), n_lig=(15, 50)), 22),   # configs[3] shapes, ragged batch
+    ("reverse_docking", dict(n_complex=4, n_poses=1, n_res=36, n_lig=30), 23),       # configs[4]: several receptors per batch
+])
+def test_baseline_workload_shapes_match_oracle(sd, name, wl, seed):
+    """Score parity against the fp32 oracle on the other BASELINE.json configurations' shapes (sizes the oracle finishes in seconds),
+    through the default kernel and the CTA-pair kernel."""
+    b = synth.make_batch(**wl, seed=seed)
+    c = conditioning(b, tr_sigma=2.5, t=0.4)
+    d = dict(b); d.update(c)
+    ref = omodel.score_model(sd, d, torch.float32)
+    for kernel in (5, 6):
+        out = run_score(make_engine(kernel, sd), b, c)
+        for k, o, r in zip(("tr", "rot", "tor", "sc"), out, ref):
+            assert o.shape == r.shape and torch.isfinite(o).all(), (name, k)
+            assert (o - r).abs().max().item() <= 2e-4 * max(r.abs().max().item(), 1e-3), (name, kernel, k)
+
+
+def test_full_size_properties_cfgA(sd):
+    """Size-independent properties at the full bench size (40 poses): (i) the batch is a disjoint union - scoring poses
+    0..19 alone gives the same bits as scoring them inside the 40-pose batch (per-graph independence, determinism);
+    (ii) the CTA-pair kernel reproduces the default kernel bit-for-bit; (iii) a 3-step trajectory is finite and moves."""
+    from diffbindfr_b200.engine import Engine
+    b40 = synth.make_batch(**synth.WORKLOADS["cfgA"], seed=3)
+    c40 = conditioning(b40)
+    e5 = make_engine(5, sd)
+    o40 = run_score(e5, b40, c40)
+    o40b = run_score(make_engine(6, sd), b40, c40)
+    for a, r in zip(o40b, o40):
+        assert torch.equal(a, r)
+    rng = np.random.default_rng(3)                   # same generator stream as make_batch(seed=3): first 20 poses of the same complex
+    base = synth.make_sample(rng, 36, 30, 12.0, 3.0)
+    samples = [base] + [synth.repose(base, rng, 3.0) for _ in range(19)]
+    b20 = synth.collate(samples)
+    o20 = run_score(e5, b20, conditioning(b20))
+    assert torch.equal(o20[0], o40[0][:20]) and torch.equal(o20[1], o40[1][:20])
+    n_tor20 = int(b20["tor_edge_mask"].sum())
+    assert torch.equal(o20[2], o40[2][:n_tor20])
+    sch, noise = _steps_and_noise(b40, 3, 5)
+    lig, a14, _, _ = e5.sample(b40, sch, Engine.pack_noise(noise[:3]))
+    torch.cuda.synchronize()
+    assert torch.isfinite(lig).all() and torch.isfinite(a14).all()
+    assert rmsd(lig.cpu(), torch.as_tensor(b40["lig_pos"])) > 1e-3

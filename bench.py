@@ -264,7 +264,7 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    kname = {0: "k_conv_tp_simt (fp32 SIMT)", 1: "k_conv_tp_tc<1> (tcgen05 3xTF32, H1 in smem)", 2: "k_conv_tp_tc<2> (tcgen05 TF32)", 3: "k_conv_tp_tc3 (tcgen05 3xTF32, H1 in TMEM)", 4: "k_conv_fused (tcgen05 3xTF32, both FC layers + fold fused)", 5: "k_conv_fused16 (tcgen05 3xFP16 split, fused)", 6: "k_conv_fused16x2 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, fused)", 7: "k_conv_fused8 (tcgen05 fp16 main + 2 e4m3 cross-term MMAs, fused)", 8: "k_conv_fused8x2 (tcgen05 cta_group::2 CTA pairs, fp16 main + 2 e4m3 cross-term MMAs, fused)"}[args.conv_kernel]
+    kname = {0: "k_conv_tp_simt (fp32 SIMT)", 1: "k_conv_tp_tc<1> (tcgen05 3xTF32, H1 in smem)", 2: "k_conv_tp_tc<2> (tcgen05 TF32)", 3: "k_conv_tp_tc3 (tcgen05 3xTF32, H1 in TMEM)", 4: "k_conv_fused (tcgen05 3xTF32, both FC layers + fold fused)", 5: "k_conv_fused16 (tcgen05 3xFP16 split, fused)", 6: "k_conv_fused16x2 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, fused)", 7: "k_conv_fused8 (tcgen05 fp16 main + 2 e4m3 cross-term MMAs, fused)", 8: "k_conv_fused8x2 (tcgen05 cta_group::2 CTA pairs, fp16 main + 2 e4m3 cross-term MMAs, fused)", 9: "k_conv_fused16wg (tcgen05 3xFP16 split, fused, two gather/fold warpgroups)"}[args.conv_kernel]
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
             "kernel": kname, "kernel_ms_per_step": tp_ms / K, "kernel_share_of_step": tp_ms / ms_total,
@@ -294,7 +294,7 @@ def main():
         cpu = cpu_baseline(n_poses=args.cpu_baseline_poses, steps=1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 4: "tf32x3", 5: "fp16x3", 6: "fp16x3", 7: "fp16+2xe4m3", 8: "fp16+2xe4m3"}[args.conv_kernel], "data": "synthetic",
+            "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 4: "tf32x3", 5: "fp16x3", 6: "fp16x3", 7: "fp16+2xe4m3", 8: "fp16+2xe4m3", 9: "fp16x3"}[args.conv_kernel], "data": "synthetic",
             "config": {"workload": f"{args.workload}: 1 complex x 40 poses x 36 residues (~300 pocket atoms) x 30 ligand atoms per GPU"
                        if args.workload == "cfgA" else f"{args.workload}: {workload_kwargs(args.workload)} per GPU",
                        "poses_per_gpu": int(b["num_graphs"]), "pocket_atoms": int(b["rec_atm_pos"].shape[0]),

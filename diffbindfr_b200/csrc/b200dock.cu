@@ -16,6 +16,7 @@
 #include "conv_fused2.cuh"
 #include "conv_fused8.cuh"
 #include "conv_fused8x2.cuh"
+#include "conv_fused_wg.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
 #include "mdn.cuh"
@@ -216,7 +217,7 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t
       F.W1hi[i] = X.W1h16[i]; F.W1lo[i] = X.W1l16[i]; F.W2hi[i] = X.W2h16[i]; F.W2lo[i] = X.W2l16[i];
       F.w2_rows[i] = X.w2_rows[i] + 144;
     }
-    rc = h->cfg.conv_kernel == 8 ? launch_conv_fused8x2(L, F, h->tp_grid, st) : h->cfg.conv_kernel == 7 ? launch_conv_fused8(L, F, h->tp_grid, st)
+    rc = h->cfg.conv_kernel == 9 ? launch_conv_fused16wg(L, F, h->tp_grid, st) : h->cfg.conv_kernel == 8 ? launch_conv_fused8x2(L, F, h->tp_grid, st) : h->cfg.conv_kernel == 7 ? launch_conv_fused8(L, F, h->tp_grid, st)
        : h->cfg.conv_kernel == 6 ? launch_conv_fused16x2(L, F, h->tp_grid, st) : launch_conv_fused16(L, F, h->tp_grid, st);
   } else if (h->cfg.conv_kernel == 4) {
     FusedExtra F{};
@@ -513,7 +514,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
   CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
   CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
-  if (conv_tc_init() || conv_fused_init() || conv_fused2_init() || conv_fused8_init() || conv_fused8x2_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  if (conv_tc_init() || conv_fused_init() || conv_fused2_init() || conv_fused8_init() || conv_fused8x2_init() || conv_fused_wg_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
   h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
   return B200_OK;
 }
@@ -614,7 +615,7 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
       const float s1 = scale_of(mx[0]), s2 = scale_of(mx[1]);
       __half* h1 = h->d_w16 + pos; __half* l1 = h1 + (size_t)192 * KH;
       __half* h2 = l1 + (size_t)192 * KH; __half* l2 = h2 + r2 * KH;
-      if (h->cfg.conv_kernel >= 7) {   // fp16 hi + e4m3 cross-term copies (the e4m3 pair takes the place of the fp16 lo array)
+      if (h->cfg.conv_kernel == 7 || h->cfg.conv_kernel == 8) {   // fp16 hi + e4m3 cross-term copies (the e4m3 pair takes the place of the fp16 lo array)
         uint8_t* q1 = reinterpret_cast<uint8_t*>(l1); uint8_t* q2 = reinterpret_cast<uint8_t*>(l2);
         k_build_w8<<<148, 256>>>(tmp, 192, 192, s1, h1, q1, q1 + (size_t)192 * KH);
         k_build_w8<<<148 * 4, 256>>>(w.W2p, w.n_cols, (int)r2, s2, h2, q2, q2 + r2 * KH);

@@ -513,7 +513,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
               for (int k8 = 0; k8 < 4; ++k8) {
                 if (ka == KATOMS - 1 && k8 >= 2) continue;   // K = 145 real columns: halves 160..191 are zero padding
                 const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + ACOLS;
-                tc::mma_f16_ts(d_tmem, a_lo, dhs[ka] + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
+                // the last K step holds only the bias column, whose A entry is an exact power of two (lo = 0): lo x hi adds nothing
+                if (!(ka == KATOMS - 1 && k8 == 1)) tc::mma_f16_ts(d_tmem, a_lo, dhs[ka] + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
                 tc::mma_f16_ts(d_tmem, a_hi, dls[ka] + (uint64_t)(k8 * 2), idesc, 1u);
                 tc::mma_f16_ts(d_tmem, a_hi, dhs[ka] + (uint64_t)(k8 * 2), idesc, 1u);
               }

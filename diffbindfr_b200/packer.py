@@ -122,7 +122,7 @@ class Plans:
                 off += m * (2 * l + 1)
                 irr += m
             ijk = np.ascontiguousarray(np.concatenate(ijk_all)); val = np.ascontiguousarray(np.concatenate(val_all))
-            ch = np.asarray(chunks_of(tp, {3: 96, 4: 96, 5: 144, 6: 144, 7: 144, 8: 144}.get(conv_kernel, CHUNK_COLS)), dtype=np.int32)
+            ch = np.asarray(chunks_of(tp, {3: 96, 4: 96, 5: 144, 6: 144, 7: 144, 8: 144, 9: 144}.get(conv_kernel, CHUNK_COLS)), dtype=np.int32)
             cc, cn, cpth = (np.ascontiguousarray(ch[:, k]) for k in range(3))
             self.keep += [ijk, val, cc, cn, cpth]
             cp.n_cg = len(ijk)

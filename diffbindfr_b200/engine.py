@@ -17,7 +17,7 @@ from . import batch as batch_mod
 from . import packer
 from .schedule import StepScalars
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200dock.so")
+_LIB_PATH = os.environ.get("B200DOCK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200dock.so")   # env override: A/B timing of kernel variants
 _lib = None
 
 EXPORTS = ["b200dock_create", "b200dock_destroy", "b200dock_last_error", "b200dock_version",

@@ -393,6 +393,59 @@ __device__ __forceinline__ void pack_store_f16(uint32_t addr_hi, uint32_t addr_l
 }
 }  // namespace tc
 
+namespace tc {
+// Software-pipelined fold of one 144-column unit (thread = edge = TMEM lane): the tensor-memory load of the next 16 (12)
+// accumulator columns is in flight while the FMAs of the current ones run, instead of a load -> wait -> FMA round trip per
+// input channel.  o[] are the thread's message accumulators; xp the gathered node row (shared memory), M = CG . sh.
+__device__ __forceinline__ void fold_unit_w48(uint32_t taddr, const float* xp, int d1, const float* M, float zs, float* o) {
+  float va[16], vb[16];
+  tmem_ld16(taddr, va);
+  float z[3];
+#pragma unroll
+  for (int uu = 0; uu < 3; ++uu) {
+    float t = xp[uu * d1] * M[0];
+    if (d1 == 3) t = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], t));
+    z[uu] = t * zs;
+  }
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {                       // 9 chunks of 16 columns: u = c / 3, w offset (c % 3) * 16
+    float* cur = (c & 1) ? vb : va;
+    float* nxt = (c & 1) ? va : vb;
+    tmem_wait_ld();
+    if (c + 1 < 9) tmem_ld16(taddr + (c + 1) * 16, nxt);
+    const float zz = z[c / 3];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[(c % 3) * 16 + j] = fmaf(cur[j], zz, o[(c % 3) * 16 + j]);
+  }
+}
+__device__ __forceinline__ void fold_unit_w12(uint32_t taddr, const float* xp, int d1, const float* M, float zs, float* o) {
+  float va[12], vb[12];
+  tmem_ld4(taddr, va); tmem_ld4(taddr + 4, va + 4); tmem_ld4(taddr + 8, va + 8);
+#pragma unroll
+  for (int uu = 0; uu < 12; ++uu) {
+    float* cur = (uu & 1) ? vb : va;
+    float* nxt = (uu & 1) ? va : vb;
+    const float x0 = xp[uu * d1];
+    float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
+    if (d1 == 3) {
+      const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
+      z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
+    }
+    z0 *= zs; z1 *= zs; z2 *= zs;
+    tmem_wait_ld();
+    if (uu + 1 < 12) {
+      const uint32_t a = taddr + (uu + 1) * 12;
+      tmem_ld4(a, nxt); tmem_ld4(a + 4, nxt + 4); tmem_ld4(a + 8, nxt + 8);
+    }
+#pragma unroll
+    for (int w = 0; w < 12; ++w) {
+      o[w * 3] = fmaf(cur[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(cur[w], z1, o[w * 3 + 1]);
+      o[w * 3 + 2] = fmaf(cur[w], z2, o[w * 3 + 2]);
+    }
+  }
+}
+}  // namespace tc
+
 // MODE 5: the fused kernel with FP16 hi/lo splits (3 x kind::f16 MMAs per K-step, K = 192 halves): same
 // error-compensation scheme, twice the tensor throughput and ~60 % of the W streaming of the TF32 variant.
 // fp16's narrow exponent is handled by exact power-of-two scaling: per conv for W1/W2 (max -> [2^9,2^10)),
@@ -694,6 +747,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
           if (L.dbg & 16) {                            // timing experiment: no fold
+          } else if (N == 144 && pa.Wd == 48) {
+            tc::fold_unit_w48(taddr, xp, d1, M, zs, o);
+          } else if (N == 144) {
+            tc::fold_unit_w12(taddr, xp, d1, M, zs, o);
           } else if (pa.Wd == 48) {
             for (int uu = 0; uu < nu; ++uu) {
               float v[48];

@@ -331,7 +331,11 @@ k_conv_fused8x2(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (pa.Wd == 48) {
+          if (N == 144 && pa.Wd == 48) {
+            tc::fold_unit_w48(taddr, xp, d1, M, zs, o);
+          } else if (N == 144) {
+            tc::fold_unit_w12(taddr, xp, d1, M, zs, o);
+          } else if (pa.Wd == 48) {
             for (int uu = 0; uu < nu; ++uu) {
               float v[48];
               tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);

@@ -82,6 +82,8 @@ struct B200Handle {
   int tp_grid = 148;
   std::vector<float> cg_dense;
   int dbg_flag = 0;
+  // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool use_side = true;
 };
 
 namespace {
@@ -267,6 +269,19 @@ int bind_plans(B200Handle* h, cudaStream_t st) {
   return B200_OK;
 }
 
+// fork: the side stream continues from the current point of `st`; join: `st` waits for everything queued on the side stream
+static inline cudaStream_t side_fork(B200Handle* h, cudaStream_t st) {
+  if (!h->use_side) return st;
+  cudaEventRecord(h->ev_fork, st);
+  cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+  return h->side;
+}
+static inline void side_join(B200Handle* h, cudaStream_t st) {
+  if (!h->use_side) return;
+  cudaEventRecord(h->ev_join, h->side);
+  cudaStreamWaitEvent(st, h->ev_join, 0);
+}
+
 int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr, float* rot, float* tor, float* sc,
                  cudaStream_t st) {
   if (!h->weights) FAIL(B200_ERR_STATE, "weights not loaded");
@@ -289,9 +304,10 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     k_graph_pre<<<dim3(b.B, 6), 64, 0, st>>>(P, c.time_emb, b.B);
     h->launches += 1;
   }
+  cudaStream_t s2 = side_fork(h, st);   // from here to the first conv layer: pocket-side work on the side stream, ligand-side on the caller's
   k_lig_node_embed<<<grid_for(b.N_l, 128, 148 * 4), 128, 0, st>>>(b.lig_node, b.lig_batch, b.N_l, W + off[B200_W_LIG_NODE],
                                                                    h->pre[0].as<float>(), h->h_lig.as<float>());
-  k_atom_node_embed<<<grid_for(b.N_a, 128, 148 * 4), 128, 0, st>>>(b.pocket_feat, b.atom_batch, b.N_a, W + off[B200_W_ATOM_EMB],
+  k_atom_node_embed<<<grid_for(b.N_a, 128, 148 * 4), 128, 0, s2>>>(b.pocket_feat, b.atom_batch, b.N_a, W + off[B200_W_ATOM_EMB],
                                                                     h->pre[2].as<float>(), h->h_atom.as<float>());
   h->launches += 2;
   // ---- graphs
@@ -303,17 +319,20 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
   G.tor_bonds = b.tor_bonds; G.n_tor = b.n_tor; G.sc_bonds = b.sc_bonds; G.n_sc = b.n_sc;
   G.lig_jmax = h->jmax_lig.as<int>(); G.atom_jmax = h->jmax_atom.as<int>();
   k_radius_cap<<<grid_for(b.N_l, 128, 148 * 8), 128, 0, st>>>(b.lig_pos, b.lig_batch, b.lig_ptr, b.N_l, 25.0f, 33, h->jmax_lig.as<int>());
-  k_radius_cap<<<grid_for(b.N_a, 128, 148 * 8), 128, 0, st>>>(b.rec_atm_pos, b.atom_batch, b.atom_ptr, b.N_a, 16.0f, 1001, h->jmax_atom.as<int>());
+  k_radius_cap<<<grid_for(b.N_a, 128, 148 * 8), 128, 0, s2>>>(b.rec_atm_pos, b.atom_batch, b.atom_ptr, b.N_a, 16.0f, 1001, h->jmax_atom.as<int>());
   h->launches += 2;
   int rc;
-  if ((rc = build_graph<G_LIG>(h, G, h->cw[0], st))) return rc;
-  if ((rc = build_graph<G_ATOM>(h, G, h->cw[1], st))) return rc;
-  if ((rc = build_graph<G_AL>(h, G, h->cw[2], st))) return rc;
-  if ((rc = build_graph<G_LA>(h, G, h->cw[3], st))) return rc;
-  edge_feat<G_LIG>(h, b, h->cw[0], edge_mlp(h, B200_W_LIG_EDGE, 10, 32), h->pre[1].as<float>(), 5.0f, st);
-  edge_feat<G_ATOM>(h, b, h->cw[1], edge_mlp(h, B200_W_ATOM_EDGE, 0, 32), h->pre[3].as<float>(), 4.0f, st);
-  edge_feat<G_AL>(h, b, h->cw[2], edge_mlp(h, B200_W_LA_EDGE, 0, 32), h->pre[4].as<float>(), 32.0f, st);
-  edge_feat<G_LA>(h, b, h->cw[3], edge_mlp(h, B200_W_LA_EDGE, 0, 32), h->pre[4].as<float>(), 32.0f, st);
+  {   // the four graph families are independent: pocket-side chains on the side stream, ligand-side chains on the caller's
+    if ((rc = build_graph<G_ATOM>(h, G, h->cw[1], s2))) return rc;
+    if ((rc = build_graph<G_LIG>(h, G, h->cw[0], st))) return rc;
+    if ((rc = build_graph<G_LA>(h, G, h->cw[3], s2))) return rc;
+    if ((rc = build_graph<G_AL>(h, G, h->cw[2], st))) return rc;
+    edge_feat<G_ATOM>(h, b, h->cw[1], edge_mlp(h, B200_W_ATOM_EDGE, 0, 32), h->pre[3].as<float>(), 4.0f, s2);
+    edge_feat<G_LIG>(h, b, h->cw[0], edge_mlp(h, B200_W_LIG_EDGE, 10, 32), h->pre[1].as<float>(), 5.0f, st);
+    edge_feat<G_LA>(h, b, h->cw[3], edge_mlp(h, B200_W_LA_EDGE, 0, 32), h->pre[4].as<float>(), 32.0f, s2);
+    edge_feat<G_AL>(h, b, h->cw[2], edge_mlp(h, B200_W_LA_EDGE, 0, 32), h->pre[4].as<float>(), 32.0f, st);
+    side_join(h, st);
+  }
   // ---- six interaction layers
   float* hl = h->h_lig.as<float>(); float* ha = h->h_atom.as<float>();
   for (int l = 0; l < h->debug_layers; ++l) {
@@ -332,36 +351,46 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     U.N = b.N_l; U.h = hl;
     U.seg[0] = h->cw[0].seg.as<int>(); U.msg[0] = h->cw[0].msg.as<float>(); U.ln[0] = h->convw[0 * 6 + l].ln;
     U.seg[1] = h->cw[2].seg.as<int>(); U.msg[1] = h->cw[2].msg.as<float>(); U.ln[1] = h->convw[2 * 6 + l].ln;
+    cudaStream_t s2 = side_fork(h, st);                                  // ligand and pocket node updates are independent
     k_node_update<4><<<grid_for(b.N_l, 2, 148 * 16), 256, 0, st>>>(U);   // long segments: 4 warps per ligand atom
     U.N = b.N_a; U.h = ha;
     U.seg[0] = h->cw[1].seg.as<int>(); U.msg[0] = h->cw[1].msg.as<float>(); U.ln[0] = h->convw[1 * 6 + l].ln;
     U.seg[1] = h->cw[3].seg.as<int>(); U.msg[1] = h->cw[3].msg.as<float>(); U.ln[1] = h->convw[3 * 6 + l].ln;
-    k_node_update<1><<<grid_for(b.N_a, 8, 148 * 8), 256, 0, st>>>(U);
+    k_node_update<1><<<grid_for(b.N_a, 8, 148 * 8), 256, 0, s2>>>(U);
+    side_join(h, st);
     h->launches += 2;
   }
-  // ---- translation / rotation heads
+  // ---- translation / rotation heads (side stream: independent of the pseudo-torque convs below)
+  cudaStream_t s3 = side_fork(h, st);
   {
-    k_centroid<<<cdiv(b.B, 64), 64, 0, st>>>(b.lig_pos, b.lig_ptr, b.B, h->centre.as<float>());
+    k_centroid<<<cdiv(b.B, 64), 64, 0, s3>>>(b.lig_pos, b.lig_ptr, b.B, h->centre.as<float>());
     CenterArgs A{};
     A.lig_pos = b.lig_pos; A.lig_batch = b.lig_batch; A.N_l = b.N_l; A.centre = h->centre.as<float>();
     A.pre = h->pre[5].as<float>(); A.mlp = edge_mlp(h, B200_W_CENTER_EDGE, 0, 32); A.fc = W + off[B200_W_FINAL_FC];
     A.h_lig = hl; A.cmsg = h->cmsg.as<float>();
-    k_center_edge<<<b.N_l, 128, 0, st>>>(A);
+    k_center_edge<<<b.N_l, 128, 0, s3>>>(A);
     CenterHeadArgs H{};
     H.cmsg = h->cmsg.as<float>(); H.lig_ptr = b.lig_ptr; H.B = b.B; H.ln = W + off[B200_W_FINAL_LN];
     H.tr_mlp = W + off[B200_W_TR_FINAL]; H.rot_mlp = W + off[B200_W_ROT_FINAL];
     H.time_emb = c.time_emb; H.tr_sigma = c.tr_sigma; H.rot_score_norm = c.rot_score_norm; H.tr = tr; H.rot = rot;
-    k_center_head<<<cdiv(b.B, 64), 64, 0, st>>>(H);
+    k_center_head<<<cdiv(b.B, 64), 64, 0, s3>>>(H);
     h->launches += 3;
   }
   // ---- pseudo-torque heads (ligand torsions, side-chain chi)
+  // graph + edge features of the side-chain graph on the side stream, of the ligand-torsion graph on the caller's stream;
+  // both tensor-product launches stay on the caller's stream (they fill the GPU; their event timing stays clean)
+  if (h->cw[5].T) {
+    if ((rc = build_graph<G_SC>(h, G, h->cw[5], s3))) return rc;
+    edge_feat<G_SC>(h, b, h->cw[5], edge_mlp(h, B200_W_SC_EDGE, 0, 0), nullptr, 4.0f, s3);
+  }
+  if (h->cw[4].T) {
+    if ((rc = build_graph<G_TOR>(h, G, h->cw[4], st))) return rc;
+    edge_feat<G_TOR>(h, b, h->cw[4], edge_mlp(h, B200_W_TOR_EDGE, 0, 0), nullptr, 5.0f, st);
+  }
   for (int which = 0; which < 2; ++which) {
     ConvWs& w = h->cw[4 + which];
+    if (which == 1) side_join(h, st);
     if (w.T == 0) continue;
-    if (which == 0) { if ((rc = build_graph<G_TOR>(h, G, w, st))) return rc; }
-    else { if ((rc = build_graph<G_SC>(h, G, w, st))) return rc; }
-    if (which == 0) edge_feat<G_TOR>(h, b, w, edge_mlp(h, B200_W_TOR_EDGE, 0, 0), nullptr, 5.0f, st);
-    else edge_feat<G_SC>(h, b, w, edge_mlp(h, B200_W_SC_EDGE, 0, 0), nullptr, 4.0f, st);
     const float* tab = which == 0 ? hl : ha;
     ConvLaunch L{};
     TcExtra X{};
@@ -433,6 +462,7 @@ int sample_device(B200Handle* h, B200Batch& b, const B200Step* steps, int n_step
     P.tr_score = h->s_tr.as<float>(); P.rot_score = h->s_rot.as<float>(); P.tor_score = h->s_tor.as<float>();
     P.z_tr = z; P.z_rot = z + 3 * b.B; P.z_tor = z + 6 * b.B; P.st = steps[s];
     P.lig_traj_out = lig_traj ? lig_traj + (size_t)s * b.N_l * 3 : nullptr;
+    cudaStream_t s2 = side_fork(h, st);           // ligand pose update and side-chain rebuild touch disjoint data
     k_lig_pose_update<<<b.B, 32, 0, st>>>(P);
     SideChainArgs S{};
     S.N_r = b.N_r; S.N_a = b.N_a; S.sequence = b.sequence; S.bb_t = b.backbone_transl; S.bb_R = b.backbone_rots;
@@ -441,8 +471,9 @@ int sample_device(B200Handle* h, B200Batch& b, const B200Step* steps, int n_step
     S.sc_score = h->s_sc.as<float>(); S.z_sc = z + 6 * b.B + b.n_tor; S.st = steps[s]; S.apply_update = 1;
     S.atom14 = (s == n_steps - 1 && atom14_out) ? atom14_out : h->atom14.as<float>();
     S.atom14_traj = atom14_traj ? atom14_traj + (size_t)s * b.N_r * 42 : nullptr;
-    k_sidechain_update<<<cdiv(b.N_r, 64), 64, 0, st>>>(S);
-    k_gather_atoms<<<grid_for(b.N_a, 256, 148 * 4), 256, 0, st>>>(S.atom14, b.atom_slot, b.N_a, b.rec_atm_pos);
+    k_sidechain_update<<<cdiv(b.N_r, 64), 64, 0, s2>>>(S);
+    k_gather_atoms<<<grid_for(b.N_a, 256, 148 * 4), 256, 0, s2>>>(S.atom14, b.atom_slot, b.N_a, b.rec_atm_pos);
+    side_join(h, st);
     h->launches += 3;
   }
   CK(cudaGetLastError());
@@ -470,6 +501,10 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   h->n_sms = prop.multiProcessorCount;
   h->tp_grid = h->n_sms;
   if (const char* g = getenv("B200DOCK_DBG")) h->dbg_flag = atoi(g);
+  if (const char* g = getenv("B200DOCK_NO_SIDE")) h->use_side = atoi(g) == 0;
+  CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   if (const char* g = getenv("B200DOCK_TP_GRID")) { int v = atoi(g); if (v > 0 && v <= h->n_sms) h->tp_grid = v; }
   for (int p = 0; p < B200_N_PLANS; ++p) {
     const B200ConvPlan& s = cfg->plans[p];
@@ -538,6 +573,9 @@ void b200dock_destroy(B200Handle* h) {
   if (h->d_w1p) cudaFree(h->d_w1p);
   if (h->d_w16) cudaFree(h->d_w16);
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
 }
 

@@ -85,3 +85,18 @@ def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], List[
     max_nl = max(int(s["lig_pos"].shape[0]) for s in samples)
     max_nr = max(int(s["sequence"].shape[0]) for s in samples)
     return gather_poses(ids, ligs, a14s, len(samples), max_nl, max_nr, group, device, scores if len(scores) == len(ids) and ids else None)
+
+
+def slice_noise(noise: Sequence[Dict[str, torch.Tensor]], graphs: Sequence[int], tor_per_graph: Sequence[int],
+                sc_per_graph: Sequence[int]) -> List[Dict[str, torch.Tensor]]:
+    """SDE noise of a sub-batch cut out of noise drawn ONCE for the reference's batch composition (SURVEY 8(e) caveat:
+    parity with a single-GPU reference run on identical seeds).  ``noise`` is the per-step list of dicts in the reference's
+    draw order (``tr`` (B,3), ``rot`` (B,3), ``tor`` (n_tor,), ``sc`` (n_sc,); scFlex.py:167-183,202-204); ``graphs`` are the
+    indices (in the reference batch) of the graphs this rank owns, in local order; ``tor_per_graph`` / ``sc_per_graph`` the
+    number of rotatable ligand bonds / existing chi angles of every graph of the reference batch."""
+    tor_off = torch.cat([torch.zeros(1, dtype=torch.long), torch.as_tensor(tor_per_graph).long().cumsum(0)])
+    sc_off = torch.cat([torch.zeros(1, dtype=torch.long), torch.as_tensor(sc_per_graph).long().cumsum(0)])
+    g = torch.as_tensor(list(graphs)).long()
+    tor_idx = torch.cat([torch.arange(int(tor_off[i]), int(tor_off[i + 1])) for i in g.tolist()]) if len(g) else torch.zeros(0, dtype=torch.long)
+    sc_idx = torch.cat([torch.arange(int(sc_off[i]), int(sc_off[i + 1])) for i in g.tolist()]) if len(g) else torch.zeros(0, dtype=torch.long)
+    return [dict(tr=z["tr"][g], rot=z["rot"][g], tor=z["tor"][tor_idx], sc=z["sc"][sc_idx]) for z in noise]

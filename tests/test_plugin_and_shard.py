@@ -151,3 +151,23 @@ def test_karmadock_plugin_forward_heterodata_layout():
     m.load_state_dict(weights.random_karmadock_state_dict(0))
     out = m(data)
     assert torch.allclose(out.cpu(), g["score"], rtol=1e-4, atol=1e-5)
+
+
+def test_slice_noise_matches_full_batch_layout():
+    """Noise drawn once for the reference batch and sliced per shard: every graph sees the same numbers whichever rank owns it."""
+    B, tor_n, sc_n = 5, [2, 0, 3, 1, 4], [7, 5, 0, 6, 2]
+    torch.manual_seed(0)
+    full = [dict(tr=torch.randn(B, 3), rot=torch.randn(B, 3), tor=torch.randn(sum(tor_n)), sc=torch.randn(sum(sc_n))) for _ in range(3)]
+    parts = {r: shard.slice_noise(full, shard.shard_indices(B, r, 2), tor_n, sc_n) for r in range(2)}
+    for r in range(2):
+        mine = shard.shard_indices(B, r, 2)
+        for s in range(3):
+            z = parts[r][s]
+            assert z["tr"].shape == (len(mine), 3) and z["tor"].numel() == sum(tor_n[i] for i in mine) and z["sc"].numel() == sum(sc_n[i] for i in mine)
+            t0 = s0 = 0
+            for k, gi in enumerate(mine):
+                assert torch.equal(z["tr"][k], full[s]["tr"][gi]) and torch.equal(z["rot"][k], full[s]["rot"][gi])
+                ft = sum(tor_n[:gi]); fs = sum(sc_n[:gi])
+                assert torch.equal(z["tor"][t0:t0 + tor_n[gi]], full[s]["tor"][ft:ft + tor_n[gi]])
+                assert torch.equal(z["sc"][s0:s0 + sc_n[gi]], full[s]["sc"][fs:fs + sc_n[gi]])
+                t0 += tor_n[gi]; s0 += sc_n[gi]

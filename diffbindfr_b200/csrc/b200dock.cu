@@ -83,6 +83,7 @@ struct B200Handle {
   std::vector<float> cg_dense;
   int dbg_flag = 0;
   // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
+  Buf trace; bool trace_on = false;
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool use_side = true;
 };
 
@@ -339,7 +340,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     const int plan = plan_of_layer(l);
     ConvLaunch L{};
     TcExtra X{};
-    L.n = 4; L.dbg = h->dbg_flag;
+    L.n = 4; L.dbg = h->dbg_flag; L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
     L.c[0] = conv_args(h, h->cw[0], 0 * 6 + l, plan, hl, hl, 0, nullptr, 9, X, 0);     // lig
     L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9, X, 1);     // atom
     L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9, X, 2);     // al: target lig, gather atom
@@ -394,7 +395,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     const float* tab = which == 0 ? hl : ha;
     ConvLaunch L{};
     TcExtra X{};
-    L.n = 1;
+    L.n = 1; L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
     L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8, X, 0);
     if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
     if ((rc = launch_tp(h, L, X, st))) return rc;
@@ -563,7 +564,7 @@ void b200dock_destroy(B200Handle* h) {
   for (auto& b : h->pre) fr(b);
   Buf* all[] = {&h->h_lig, &h->h_atom, &h->jmax_lig, &h->jmax_atom, &h->centre, &h->cmsg, &h->s_tr, &h->s_rot, &h->s_tor,
                 &h->s_sc, &h->atom14, &h->errflag, &h->c_temb, &h->c_trs, &h->c_rotn, &h->c_torn, &h->c_scn,
-                &h->temb_steps, &h->mdn_w, &h->mdn_A, &h->mdn_B, &h->enc_w, &h->enc_ws, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
+                &h->temb_steps, &h->mdn_w, &h->mdn_A, &h->mdn_B, &h->enc_w, &h->enc_ws, &h->trace, &h->dev_in, &h->dev_noise, &h->dev_lig_out, &h->dev_a14_out};
   for (Buf* b : all) fr(*b);
   if (h->pinned_in.p) cudaFreeHost(h->pinned_in.p);
   if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
@@ -976,6 +977,7 @@ int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t 
   const B200Batch& b = h->last_batch;
   const void* src = nullptr; size_t bytes = 0;
   if (what == B200_TAP_H_LIG) { src = h->h_lig.p; bytes = (size_t)b.N_l * HS * 4; }
+  else if (what == 7) { src = h->trace.p; bytes = h->trace.p ? (size_t)148 * 32 * 8 : 0; }
   else if (what == B200_TAP_H_ATOM) { src = h->h_atom.p; bytes = (size_t)b.N_a * HS * 4; }
   else if (what == B200_TAP_EDGES) {
     if (arg < 0 || arg > 5) return B200_ERR_INVALID;
@@ -1015,6 +1017,13 @@ int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t 
 int b200dock_debug_set(B200Handle* h, int key, int value) {
   if (!h) return B200_ERR_INVALID;
   if (key == 0) { h->debug_layers = value; return B200_OK; }
+  if (key == 1) {   // wait-cycle accounting of the fused conv kernel (mode 5): 148 CTAs x 32 counters, accumulated over launches
+    CK(cudaSetDevice(h->device));
+    ENS(h->trace, (size_t)148 * 32 * 8);
+    CK(cudaMemset(h->trace.p, 0, (size_t)148 * 32 * 8));
+    h->trace_on = value != 0;
+    return B200_OK;
+  }
   return B200_ERR_INVALID;
 }
 

@@ -62,7 +62,7 @@ struct ConvArgs {
   float* msg;               // [E_pad][HS]
   float inv_s1, inv_s2;     // fp16 mode: inverse power-of-two scales of the packed W1 / W2
 };
-struct ConvLaunch { ConvArgs c[4]; int n; int dbg; };   // dbg: timing experiments only (B200DOCK_DBG)
+struct ConvLaunch { ConvArgs c[4]; int n; int dbg; long long* trace; };   // dbg / trace: timing experiments only (B200DOCK_DBG, debug_set(1))
 
 #define PRO_THREADS 256
 #define PRO_XS_STRIDE 132    // floats per k-row of the transposed edge-input tile (128 + pad, 16B aligned)

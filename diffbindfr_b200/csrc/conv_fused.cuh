@@ -382,11 +382,12 @@ __device__ __forceinline__ float row_scale(float mx) {
 __device__ __forceinline__ void pack_store_f16(uint32_t addr_hi, uint32_t addr_lo, const float* v) {
   float ph[32], pl[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    __half h0 = __float2half_rn(v[2 * c]), h1 = __float2half_rn(v[2 * c + 1]);
-    __half l0 = __float2half_rn(v[2 * c] - __half2float(h0)), l1 = __float2half_rn(v[2 * c + 1] - __half2float(h1));
-    ph[c] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
-    pl[c] = __uint_as_float((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16));
+  for (int c = 0; c < 32; ++c) {                       // packed conversions: one cvt.rn.f16x2.f32 per pair and per term
+    const __half2 h = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v[2 * c] - hf.x, v[2 * c + 1] - hf.y);
+    ph[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+    pl[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
   }
   tmem_st32(addr_hi, ph);
   tmem_st32(addr_lo, pl);
@@ -528,6 +529,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
     static_assert(F16_NST == 3, "stage == k-atom mapping");
     tc::Phase db;
     uint32_t xpar = 0, hpar = 0, bpar = 0;
+    long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // wait-cycle accounting (L.trace): x_full, h_full, d_empty, b_full[0..2], -, total
+    const bool tr = L.trace != nullptr;
+    const long long t_begin = tr ? clock64() : 0;
+#define TRW(i, stmt) do { if (tr) { long long _t = clock64(); stmt; tw[i] += clock64() - _t; } else { stmt; } } while (0)
     uint64_t dhs[KATOMS], dls[KATOMS];
 #pragma unroll
     for (int ka = 0; ka < KATOMS; ++ka) {
@@ -542,12 +547,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
       int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
       tiles_before += ntile;
       for (int tile = first; tile < ntile; tile += gridDim.x) {
-        tc::mbar_wait(x_full, xpar);
+        TRW(0, tc::mbar_wait(x_full, xpar));
         xpar ^= 1;
         tc::fence_after();
         for (int unit = -1; unit < P.n_chunks; ++unit) {
           if (unit == 0) {                              // H1 must be in tensor memory before the W2 units
-            tc::mbar_wait(h_full, hpar);
+            TRW(1, tc::mbar_wait(h_full, hpar));
             hpar ^= 1;
             tc::fence_after();
           }
@@ -555,11 +560,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const uint32_t idesc = tc::make_idesc_f16(128, N);
           const uint32_t d_tmem = tmem_base + (uint32_t)(D0 + db.idx * BN);
           const bool last_unit = (unit + 1 == P.n_chunks);
-          tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
+          TRW(2, tc::mbar_wait(&d_empty[db.idx], db.par ^ 1));
           tc::fence_after();
 #pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
-            tc::mbar_wait(&b_full[ka], bpar);
+            TRW(3 + ka, tc::mbar_wait(&b_full[ka], bpar));
             if (!(L.dbg & 8)) tc::fence_after();
             if (tc::elect_one()) {
 #pragma unroll
@@ -584,6 +589,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         }
       }
     }
+    if (tr && lane == 0) {
+      tw[7] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + i), (unsigned long long)tw[i]);
+    }
   } else if (warp >= 4) {
     // ================================================== gather / H1 / epilogue warps (thread = edge)
     const int q = warp & 3;
@@ -593,6 +602,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
     tc::Phase db;
     uint32_t apar = 0;
     int tiles_before = 0;
+    // epilogue accounting (L.trace, slots 8..15): a_empty wait, xin gather+store, x1 gather, D1 wait, H1 conversion, fold d_full waits, fold compute, total
+    long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool tr = L.trace != nullptr;
+    const long long t_begin = tr ? clock64() : 0;
+    long long tmark = 0;
+#define TRE_BEGIN() do { if (tr) tmark = clock64(); } while (0)
+#define TRE_END(i) do { if (tr) { long long _n = clock64(); te[i] += _n - tmark; tmark = _n; } } while (0)
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
       const DevPlan& P = c_plans[C.plan];
@@ -604,7 +620,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         const int s = C.es[e], d = C.ed[e];
         float sx = 1.0f, shh = 1.0f;
         // ---- 1. xin -> tensor memory
+        TRE_BEGIN();
         tc::mbar_wait(a_empty, apar ^ 1);
+        TRE_END(0);
         apar ^= 1;
         tc::fence_after();
         {
@@ -651,31 +669,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           tc::tmem_wait_st();
           tc::fence_before();
           tc::mbar_arrive(x_full);
+          TRE_END(1);
         }
-        // ---- x1 row -> per-thread scratch, edge harmonics -> registers
-        {
-          const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
-          const int nq = (P.in_dim + 3) >> 2;            // 12, 21, 30 or 42 float4
-#pragma unroll 1
-          for (int q0 = (L.dbg & 4) ? nq : 0; q0 < nq; q0 += 14) {
-            float4 f[14];
+        // ---- x1 row -> per-thread scratch: the first 14 float4 now (they fit in the shadow of the W1 MMAs), the rest after the H1
+        //      conversion (the tensor pipe then has two W2 units of runway), so the gather never delays H1
+        const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
+        const int nq = (P.in_dim + 3) >> 2;              // 12, 21, 30 or 42 float4
+        auto x1_batch = [&](int q0) {
+          float4 f[14];
 #pragma unroll
-            for (int j = 0; j < 14; ++j) f[j] = (q0 + j < nq) ? __ldg(px + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 14; ++j) f[j] = (q0 + j < nq) ? __ldg(px + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 14; ++j)
-              if (q0 + j < nq) {
-                float* o = xrow + 4 * (q0 + j);
-                o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
-              }
-          }
-        }
+          for (int j = 0; j < 14; ++j)
+            if (q0 + j < nq) {
+              float* o = xrow + 4 * (q0 + j);
+              o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
+            }
+        };
+        if (!(L.dbg & 4)) x1_batch(0);
         float shv[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
+        TRE_END(2);
         // ---- 3. D1 -> relu -> H1 hi/lo -> tensor memory
         {
           tc::Phase p0 = db; tc::advance(db, 2);
           tc::mbar_wait(&d_full[p0.idx], p0.par);
+          TRE_END(3);
           tc::fence_after();
           const uint32_t t0 = lane_base + (uint32_t)(D0 + p0.idx * BN);
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
@@ -711,6 +731,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&d_empty[p0.idx]);
           tc::mbar_arrive(h_full);
+          TRE_END(4);
+        }
+        if (!(L.dbg & 4)) {
+#pragma unroll 1
+          for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
         }
         // ---- 5. W2 units: fold with Z computed on the fly
         float* mrow = C.msg + (size_t)e * HS;
@@ -742,7 +767,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           }
           const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
           const float* xp = xrow + pa.in1_off + u0 * d1;
+          TRE_END(6);
           tc::mbar_wait(&d_full[db.idx], db.par);
+          TRE_END(5);
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
@@ -795,7 +822,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             }
           }
         }
+        TRE_END(6);
       }
+    }
+    if (tr && warp == 4 && lane == 0) {
+      te[7] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + 8 + i), (unsigned long long)te[i]);
     }
   }
   tc::fence_before();
@@ -804,6 +836,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
     tc::fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+#undef TRW
+#undef TRE_BEGIN
+#undef TRE_END
 }
 
 struct FusedExtra { const float* W1hi[4]; const float* W1lo[4]; const float* W2lo[4]; uint64_t w2_rows[4]; };

@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfgA")
-    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "5")))
+    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "6")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mdn", action="store_true", help="skip the MDN rescoring measurement")
     ap.add_argument("--fast-kernel", type=int, default=8, help="also time this opt-in conv kernel (0 = skip); reported under fast_mode")
@@ -260,8 +260,8 @@ def main():
     achieved = f_tp * K / (tp_ms * 1e-3) / 1e12 if tp_ms > 0 else None
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_extract.py)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fused16_ncu_step.json")))
-        if args.conv_kernel == 5 and args.workload == "cfgA":
+        tj = json.load(open(os.path.join(ROOT, "profiles", {5: "r01_fused16_ncu_step.json", 6: "r01_fused16x2_ncu_step.json", 8: "r01_fused8x2_ncu_step.json"}[args.conv_kernel])))
+        if args.workload == "cfgA":
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass

@@ -48,9 +48,10 @@ __device__ __forceinline__ void pack_store_f8x(uint32_t addr16, uint32_t addr8h,
   float p16[32], p8h[16], p8l[16];
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    const __half h0 = __float2half_rn(v[2 * c]), h1 = __float2half_rn(v[2 * c + 1]);
-    const float f0 = __half2float(h0), f1 = __half2float(h1);
-    p16[c] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
+    const __half2 h = __floats2half2_rn(v[2 * c], v[2 * c + 1]);      // packed conversion: one cvt.rn.f16x2.f32 per pair
+    const float2 hf = __half22float2(h);
+    const float f0 = hf.x, f1 = hf.y;
+    p16[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
     const uint32_t qh = __nv_cvt_float2_to_fp8x2(make_float2(f0 * 0.0625f, f1 * 0.0625f), __NV_SATFINITE, __NV_E4M3);
     const uint32_t ql = __nv_cvt_float2_to_fp8x2(make_float2((v[2 * c] - f0) * 256.0f, (v[2 * c + 1] - f1) * 256.0f), __NV_SATFINITE, __NV_E4M3);
     if (c & 1) {

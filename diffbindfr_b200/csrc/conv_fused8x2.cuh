@@ -238,23 +238,22 @@ k_conv_fused8x2(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(x_full0);
         }
-        // ---- x1 row -> per-thread scratch, edge harmonics -> registers
-        {
-          const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
-          const int nq = (P.in_dim + 3) >> 2;            // 12, 21, 30 or 42 float4
-#pragma unroll 1
-          for (int q0 = 0; q0 < nq; q0 += 14) {
-            float4 f[14];
+        // ---- x1 row -> per-thread scratch: the first 14 float4 now (they fit in the shadow of the W1 MMAs), the rest after the H1
+        //      conversion (the tensor pipe then has two W2 units of runway), so the gather never delays H1
+        const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
+        const int nq = (P.in_dim + 3) >> 2;              // 12, 21, 30 or 42 float4
+        auto x1_batch = [&](int q0) {
+          float4 f[14];
 #pragma unroll
-            for (int j = 0; j < 14; ++j) f[j] = (q0 + j < nq) ? __ldg(px + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 14; ++j) f[j] = (q0 + j < nq) ? __ldg(px + q0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 14; ++j)
-              if (q0 + j < nq) {
-                float* o = xrow + 4 * (q0 + j);
-                o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
-              }
-          }
-        }
+          for (int j = 0; j < 14; ++j)
+            if (q0 + j < nq) {
+              float* o = xrow + 4 * (q0 + j);
+              o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
+            }
+        };
+        x1_batch(0);
         float shv[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
@@ -297,6 +296,8 @@ k_conv_fused8x2(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
           __syncwarp();
           if (lane == 0) { tc::mbar_arrive_cluster(d_empty0[p0.idx]); tc::mbar_arrive_cluster(h_full0); }
         }
+#pragma unroll 1
+        for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
         // ---- 5. W2 units: fold with Z computed on the fly
         float* mrow = C.msg + (size_t)e * HS;
         float o[48];

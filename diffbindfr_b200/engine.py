@@ -107,9 +107,10 @@ class Engine:
     2 tcgen05 single TF32 (fast, ~1e-3), 3 tcgen05 3xTF32 with H1 resident in tensor memory,
     4 fully fused tcgen05 3xTF32 conv (both FC layers + fold in one kernel),
     5 the fused kernel with FP16 hi/lo error-compensated MMAs and per-row scaling (fp32-grade),
-    6 mode 5 on CTA pairs (tcgen05 cta_group::2: the weight operand is split across two SMs)."""
+    6 mode 5 on CTA pairs (tcgen05 cta_group::2: the weight operand is split across two SMs; bit-identical to 5; default),
+    7 / 8 fp16 main product + two e4m3 cross-term MMAs (single CTA / CTA pairs; opt-in, ~5e-5), 9 mode 5 with two fold warpgroups."""
 
-    def __init__(self, device: int = 0, conv_kernel: int = 5):
+    def __init__(self, device: int = 0, conv_kernel: int = 6):
         if not torch.cuda.is_available():
             raise RuntimeError("diffbindfr_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = load_library()

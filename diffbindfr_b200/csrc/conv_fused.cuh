@@ -414,11 +414,17 @@ __device__ __forceinline__ void fold_unit_w48(uint32_t taddr, const float* xp, i
     float* nxt = (c & 1) ? va : vb;
     tmem_wait_ld();
     if (c + 1 < 9) tmem_ld16(taddr + (c + 1) * 16, nxt);
-    const float zz = z[c / 3];
+    const float2 zz = make_float2(z[c / 3], z[c / 3]);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[(c % 3) * 16 + j] = fmaf(cur[j], zz, o[(c % 3) * 16 + j]);
+    for (int j = 0; j < 16; j += 2) {                 // packed fp32 FMAs (FFMA2, sm_100): two accumulators per instruction, IEEE per lane
+      const int w = (c % 3) * 16 + j;
+      const float2 r = __ffma2_rn(make_float2(cur[j], cur[j + 1]), zz, make_float2(o[w], o[w + 1]));
+      o[w] = r.x; o[w + 1] = r.y;
+    }
   }
 }
+// Wd = 12, three output components per channel: accumulators are kept COMPONENT-MAJOR, o[k * 12 + w] (the caller un-permutes when
+// it stores the block), so that channel pairs (w, w+1) of one component are adjacent registers for the packed FMAs.
 __device__ __forceinline__ void fold_unit_w12(uint32_t taddr, const float* xp, int d1, const float* M, float zs, float* o) {
   float va[12], vb[12];
   tmem_ld4(taddr, va); tmem_ld4(taddr + 4, va + 4); tmem_ld4(taddr + 8, va + 8);
@@ -432,17 +438,19 @@ __device__ __forceinline__ void fold_unit_w12(uint32_t taddr, const float* xp, i
       const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
       z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
     }
-    z0 *= zs; z1 *= zs; z2 *= zs;
+    const float2 zz[3] = {make_float2(z0 * zs, z0 * zs), make_float2(z1 * zs, z1 * zs), make_float2(z2 * zs, z2 * zs)};
     tmem_wait_ld();
     if (uu + 1 < 12) {
       const uint32_t a = taddr + (uu + 1) * 12;
       tmem_ld4(a, nxt); tmem_ld4(a + 4, nxt + 4); tmem_ld4(a + 8, nxt + 8);
     }
 #pragma unroll
-    for (int w = 0; w < 12; ++w) {
-      o[w * 3] = fmaf(cur[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(cur[w], z1, o[w * 3 + 1]);
-      o[w * 3 + 2] = fmaf(cur[w], z2, o[w * 3 + 2]);
-    }
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int w = 0; w < 12; w += 2) {
+        const float2 r = __ffma2_rn(make_float2(cur[w], cur[w + 1]), zz[k], make_float2(o[k * 12 + w], o[k * 12 + w + 1]));
+        o[k * 12 + w] = r.x; o[k * 12 + w + 1] = r.y;
+      }
   }
 }
 }  // namespace tc
@@ -774,40 +782,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
           if (L.dbg & 16) {                            // timing experiment: no fold
-          } else if (N == 144 && pa.Wd == 48) {
-            tc::fold_unit_w48(taddr, xp, d1, M, zs, o);
-          } else if (N == 144) {
-            tc::fold_unit_w12(taddr, xp, d1, M, zs, o);
-          } else if (pa.Wd == 48) {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[48];
-              tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
-              float z = xp[uu * d1] * M[0];
-              if (d1 == 3) z = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], z));
-              z *= zs;
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 48; ++w) o[w] = fmaf(v[w], z, o[w]);
-            }
-          } else {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[12];
-              tc::tmem_ld4(taddr + uu * 12, v); tc::tmem_ld4(taddr + uu * 12 + 4, v + 4); tc::tmem_ld4(taddr + uu * 12 + 8, v + 8);
-              const float x0 = xp[uu * d1];
-              float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
-              if (d1 == 3) {
-                const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
-                z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
-              }
-              z0 *= zs; z1 *= zs; z2 *= zs;
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 12; ++w) {
-                o[w * 3] = fmaf(v[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(v[w], z1, o[w * 3 + 1]);
-                o[w * 3 + 2] = fmaf(v[w], z2, o[w * 3 + 2]);
-              }
-            }
-          }
+          } else if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);   // every unit is 144 columns wide (packer.py asserts it)
+          else tc::fold_unit_w12(taddr, xp, d1, M, zs, o);                     // accumulators component-major, see the store below
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&d_empty[db.idx]);
@@ -817,9 +793,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             const int nout = (pa.Wd == 48) ? 48 : 36;
 #pragma unroll
             for (int i = 0; i < 48; i += 4) {
-              if (i < nout) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-              o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
+              if (i < nout) {
+                if (pa.Wd == 48) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                else *reinterpret_cast<float4*>(mrow + pa.out_off + i) =         // message element i = (channel i / 3, component i % 3)
+                    make_float4(o[(i % 3) * 12 + i / 3], o[((i + 1) % 3) * 12 + (i + 1) / 3], o[((i + 2) % 3) * 12 + (i + 2) / 3],
+                                o[((i + 3) % 3) * 12 + (i + 3) / 3]);
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 48; ++i) o[i] = 0.0f;
           }
         }
         TRE_END(6);

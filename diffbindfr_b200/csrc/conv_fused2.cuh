@@ -152,6 +152,10 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
     // Every unit consumes KATOMS = 3 ring stages and NST = 6, so stage = (unit parity) * 3 + k-atom: descriptors hoisted.
     tc::Phase db;
     uint32_t xpar = 0, hpar = 0, bpar0 = 0, bpar1 = 0;
+    long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // wait-cycle accounting (L.trace): x_full, h_full, d_empty, b_full[k-atom 0..2], -, total
+    const bool tr = L.trace != nullptr;
+    const long long t_begin = tr ? clock64() : 0;
+#define TRW(i, stmt) do { if (tr) { long long _t = clock64(); stmt; tw[i] += clock64() - _t; } else { stmt; } } while (0)
     uint64_t dhs[NST], dls[NST];
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
@@ -169,24 +173,24 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
       int first = (int)((cid + nclus - (pairs_before % nclus)) % nclus);
       pairs_before += npair;
       for (int pair = first; pair < npair; pair += nclus) {
-        tc::mbar_wait_cluster(x_full, xpar);
+        TRW(0, tc::mbar_wait_cluster(x_full, xpar));
         xpar ^= 1;
         tc::fence_after();
         for (int unit = -1; unit < P.n_chunks; ++unit, ++useq) {
           if (unit == 0) {                              // H1 must be in tensor memory before the W2 units
-            tc::mbar_wait_cluster(h_full, hpar);
+            TRW(1, tc::mbar_wait_cluster(h_full, hpar));
             hpar ^= 1;
             tc::fence_after();
           }
           const uint32_t half = useq & 1;
           const uint32_t d_tmem = tmem_base + (uint32_t)(D0 + db.idx * BN);
           const bool last_unit = (unit + 1 == P.n_chunks);
-          tc::mbar_wait_cluster(&d_empty[db.idx], db.par ^ 1);
+          TRW(2, tc::mbar_wait_cluster(&d_empty[db.idx], db.par ^ 1));
           tc::fence_after();
 #pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
             const int s = half ? KATOMS + ka : ka;
-            tc::mbar_wait_cluster(&b_full[s], half ? bpar1 : bpar0);
+            TRW(3 + ka, tc::mbar_wait_cluster(&b_full[s], half ? bpar1 : bpar0));
             tc::fence_after();
             if (tc::elect_one()) {
               const uint64_t dh = half ? dhs[KATOMS + ka] : dhs[ka], dl = half ? dls[KATOMS + ka] : dls[ka];
@@ -212,6 +216,11 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
         }
       }
     }
+    if (tr && lane == 0) {
+      tw[7] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + i), (unsigned long long)tw[i]);
+    }
+#undef TRW
   } else if (warp >= 4) {
     // ================================================== gather / H1 / epilogue warps (thread = edge), both CTAs
     const int q = warp & 3;
@@ -223,6 +232,13 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
     tc::Phase db;
     uint32_t apar = 0;
     int pairs_before = 0;
+    // fold-warp accounting (L.trace slots 8..15): a_empty wait, xin gather+store, x1 gather, D1 wait, H1 conversion, fold d_full waits, fold compute, total
+    long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool tr = L.trace != nullptr;
+    const long long t_begin = tr ? clock64() : 0;
+    long long tmark = 0;
+#define TRE_BEGIN() do { if (tr) tmark = clock64(); } while (0)
+#define TRE_END(i) do { if (tr) { long long _n = clock64(); te[i] += _n - tmark; tmark = _n; } } while (0)
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
       const DevPlan& P = c_plans[C.plan];
@@ -238,7 +254,9 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
         const int s = C.es[e], d = C.ed[e];
         float sx = 1.0f, shh = 1.0f;
         // ---- 1. xin -> tensor memory
+        TRE_BEGIN();
         tc::mbar_wait_cluster(a_empty, apar ^ 1);
+        TRE_END(0);
         apar ^= 1;
         tc::fence_after();
         {
@@ -284,6 +302,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(x_full0);
+          TRE_END(1);
         }
         // ---- x1 row -> per-thread scratch: the first 14 float4 now (they fit in the shadow of the W1 MMAs), the rest after the H1
         //      conversion (the tensor pipe then has two W2 units of runway), so the gather never delays H1
@@ -304,10 +323,12 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
         float shv[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
+        TRE_END(2);
         // ---- 3. D1 -> relu -> H1 hi/lo -> tensor memory
         {
           tc::Phase p0 = db; tc::advance(db, 2);
           tc::mbar_wait_cluster(&d_full[p0.idx], p0.par);
+          TRE_END(3);
           tc::fence_after();
           const uint32_t t0 = lane_base + (uint32_t)(D0 + p0.idx * BN);
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
@@ -342,6 +363,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           tc::fence_before();
           __syncwarp();
           if (lane == 0) { tc::mbar_arrive_cluster(d_empty0[p0.idx]); tc::mbar_arrive_cluster(h_full0); }
+          TRE_END(4);
         }
 #pragma unroll 1
         for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
@@ -375,40 +397,14 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           }
           const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
           const float* xp = xrow + pa.in1_off + u0 * d1;
+          TRE_END(6);
           tc::mbar_wait_cluster(&d_full[db.idx], db.par);
+          TRE_END(5);
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (pa.Wd == 48) {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[48];
-              tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
-              float z = xp[uu * d1] * M[0];
-              if (d1 == 3) z = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], z));
-              z *= zs;
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 48; ++w) o[w] = fmaf(v[w], z, o[w]);
-            }
-          } else {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[12];
-              tc::tmem_ld4(taddr + uu * 12, v); tc::tmem_ld4(taddr + uu * 12 + 4, v + 4); tc::tmem_ld4(taddr + uu * 12 + 8, v + 8);
-              const float x0 = xp[uu * d1];
-              float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
-              if (d1 == 3) {
-                const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
-                z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
-              }
-              z0 *= zs; z1 *= zs; z2 *= zs;
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 12; ++w) {
-                o[w * 3] = fmaf(v[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(v[w], z1, o[w * 3 + 1]);
-                o[w * 3 + 2] = fmaf(v[w], z2, o[w * 3 + 2]);
-              }
-            }
-          }
+          if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);        // every unit is 144 columns wide (packer.py asserts it)
+          else tc::fold_unit_w12(taddr, xp, d1, M, zs, o);                     // accumulators component-major, see the store below
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(d_empty0[db.idx]);
@@ -418,13 +414,25 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
             const int nout = (pa.Wd == 48) ? 48 : 36;
 #pragma unroll
             for (int i = 0; i < 48; i += 4) {
-              if (i < nout && live) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-              o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
+              if (i < nout && live) {
+                if (pa.Wd == 48) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                else *reinterpret_cast<float4*>(mrow + pa.out_off + i) =         // message element i = (channel i / 3, component i % 3)
+                    make_float4(o[(i % 3) * 12 + i / 3], o[((i + 1) % 3) * 12 + (i + 1) / 3], o[((i + 2) % 3) * 12 + (i + 2) / 3],
+                                o[((i + 3) % 3) * 12 + (i + 3) / 3]);
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 48; ++i) o[i] = 0.0f;
           }
         }
       }
     }
+    if (tr && warp == 4 && lane == 0) {
+      te[7] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + 8 + i), (unsigned long long)te[i]);
+    }
+#undef TRE_BEGIN
+#undef TRE_END
     tc::mbar_wait_cluster(a_empty, apar ^ 1);    // tail: the last tile's release has landed in this CTA
   }
   tc::fence_before();

@@ -332,40 +332,8 @@ k_conv_fused8x2(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (N == 144 && pa.Wd == 48) {
-            tc::fold_unit_w48(taddr, xp, d1, M, zs, o);
-          } else if (N == 144) {
-            tc::fold_unit_w12(taddr, xp, d1, M, zs, o);
-          } else if (pa.Wd == 48) {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[48];
-              tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
-              float z = xp[uu * d1] * M[0];
-              if (d1 == 3) z = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], z));
-              z *= zs;
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 48; ++w) o[w] = fmaf(v[w], z, o[w]);
-            }
-          } else {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[12];
-              tc::tmem_ld4(taddr + uu * 12, v); tc::tmem_ld4(taddr + uu * 12 + 4, v + 4); tc::tmem_ld4(taddr + uu * 12 + 8, v + 8);
-              const float x0 = xp[uu * d1];
-              float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
-              if (d1 == 3) {
-                const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
-                z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
-              }
-              z0 *= zs; z1 *= zs; z2 *= zs;
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 12; ++w) {
-                o[w * 3] = fmaf(v[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(v[w], z1, o[w * 3 + 1]);
-                o[w * 3 + 2] = fmaf(v[w], z2, o[w * 3 + 2]);
-              }
-            }
-          }
+          if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);        // every unit is 144 columns wide (packer.py asserts it)
+          else tc::fold_unit_w12(taddr, xp, d1, M, zs, o);                     // accumulators component-major, see the store below
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(d_empty0[db.idx]);
@@ -375,9 +343,15 @@ k_conv_fused8x2(ConvLaunch L, const __grid_constant__ Fused8Maps maps) {
             const int nout = (pa.Wd == 48) ? 48 : 36;
 #pragma unroll
             for (int i = 0; i < 48; i += 4) {
-              if (i < nout && live) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-              o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
+              if (i < nout && live) {
+                if (pa.Wd == 48) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                else *reinterpret_cast<float4*>(mrow + pa.out_off + i) =         // message element i = (channel i / 3, component i % 3)
+                    make_float4(o[(i % 3) * 12 + i / 3], o[((i + 1) % 3) * 12 + (i + 1) / 3], o[((i + 2) % 3) * 12 + (i + 2) / 3],
+                                o[((i + 3) % 3) * 12 + (i + 3) / 3]);
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 48; ++i) o[i] = 0.0f;
           }
         }
       }

@@ -124,6 +124,7 @@ class Plans:
             ijk = np.ascontiguousarray(np.concatenate(ijk_all)); val = np.ascontiguousarray(np.concatenate(val_all))
             ch = np.asarray(chunks_of(tp, {3: 96, 4: 96, 5: 144, 6: 144, 7: 144, 8: 144, 9: 144}.get(conv_kernel, CHUNK_COLS)), dtype=np.int32)
             cc, cn, cpth = (np.ascontiguousarray(ch[:, k]) for k in range(3))
+            assert conv_kernel < 5 or pid == 5 or (cn == 144).all(), "the fused kernels fold whole 144-column units"   # plan 5 = centre conv (own kernel)
             self.keep += [ijk, val, cc, cn, cpth]
             cp.n_cg = len(ijk)
             cp.cg_ijk = ijk.ctypes.data_as(C.POINTER(C.c_int32)); cp.cg_val = val.ctypes.data_as(C.POINTER(C.c_float))

@@ -538,9 +538,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
     tc::Phase db;
     uint32_t xpar = 0, hpar = 0, bpar = 0;
     long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // wait-cycle accounting (L.trace): x_full, h_full, d_empty, b_full[0..2], -, total
+#ifdef B200DOCK_TRACE
     const bool tr = L.trace != nullptr;
     const long long t_begin = tr ? clock64() : 0;
 #define TRW(i, stmt) do { if (tr) { long long _t = clock64(); stmt; tw[i] += clock64() - _t; } else { stmt; } } while (0)
+#else                                                    // production build: no accounting code at all
+    constexpr bool tr = false;
+    const long long t_begin = 0;
+#define TRW(i, stmt) do { stmt; } while (0)
+#endif
     uint64_t dhs[KATOMS], dls[KATOMS];
 #pragma unroll
     for (int ka = 0; ka < KATOMS; ++ka) {
@@ -612,11 +618,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
     int tiles_before = 0;
     // epilogue accounting (L.trace, slots 8..15): a_empty wait, xin gather+store, x1 gather, D1 wait, H1 conversion, fold d_full waits, fold compute, total
     long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef B200DOCK_TRACE
     const bool tr = L.trace != nullptr;
     const long long t_begin = tr ? clock64() : 0;
     long long tmark = 0;
 #define TRE_BEGIN() do { if (tr) tmark = clock64(); } while (0)
 #define TRE_END(i) do { if (tr) { long long _n = clock64(); te[i] += _n - tmark; tmark = _n; } } while (0)
+#else
+    constexpr bool tr = false;
+    const long long t_begin = 0;
+#define TRE_BEGIN() do { } while (0)
+#define TRE_END(i) do { } while (0)
+#endif
     for (int ci = 0; ci < L.n; ++ci) {
       const ConvArgs& C = L.c[ci];
       const DevPlan& P = c_plans[C.plan];

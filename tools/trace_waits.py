@@ -1,6 +1,9 @@
 """Where the fused conv kernel (modes 5 / 6) waits: cycle counters accumulated inside the kernel (b200dock_debug_set(1, 1)).
 Run on a B200:  python tools/trace_waits.py [steps] [kernel]"""
 import os, sys
+_T = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffbindfr_b200", "libb200dock_trace.so")
+assert os.path.exists(_T), "build the traced library first: python __graft_entry__.py --trace"
+os.environ["B200DOCK_LIB"] = _T
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diffbindfr_b200 import synth, weights, schedule

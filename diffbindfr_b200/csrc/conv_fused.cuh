@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         int cur_path = -1;
         float M[9];
         for (int ch = 0; ch < P.n_chunks; ++ch) {
-          const int col0 = P.chunk_col[ch], N = P.chunk_n[ch];
+          const int col0 = P.chunk_col[ch];
           const int pidx = P.chunk_path[ch];
           const B200Path pa = P.paths[pidx];
           const int d1 = 2 * pa.l1 + 1;
@@ -786,7 +786,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
                 for (int k = 0; k < 3; ++k) M[i * 3 + k] = fmaf(cg[(i * 5 + j) * 3 + k], sj, M[i * 3 + k]);
             }
           }
-          const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
+          const int rel = col0 - pa.col_off;             // first input channel of this unit: Wd is 48 or 12 (constant divisors)
+          const int u0 = (pa.Wd == 48) ? rel / 48 : rel / 12;
           const float* xp = xrow + pa.in1_off + u0 * d1;
           TRE_END(6);
           tc::mbar_wait(&d_full[db.idx], db.par);

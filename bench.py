@@ -292,7 +292,9 @@ def main():
         fast = {"conv_kernel": args.fast_kernel, "dtype": "fp16+2xe4m3", "value": 1e3 / fms, "unit": UNIT, "ms_per_step": fms, "n_gpus": 1,
                 "ligand_rmsd_vs_default_after_K_steps_A": dev_lig,
                 "note": "opt-in mode: fp16 main product + two e4m3 cross-term MMAs on CTA pairs; reference fixtures: scores within 8e-5, "
-                        "20-step trajectory within 2e-4 A (bars: 2e-4 / 1e-3 A)"}
+                        "20-step trajectory within 2e-4 A (bars: 2e-4 / 1e-3 A); cfg-A-shape poses: 3.7e-5 A vs the fp32 oracle over 10 steps "
+                        "(default kernel 6.5e-6 A); the larger distance to the default run over 40 poses x 20 steps comes from radius-graph "
+                        "edges flipping at their cutoff in a few poses (DESIGN.md section 5)"}
     mdn = None
     if not args.no_mdn:
         # MDN rescoring of the 40 final poses: device featuriser + GVP / graph-transformer encoders + mixture head

@@ -89,7 +89,10 @@ typedef struct {
   B200ConvPlan plans[B200_N_PLANS];
   int32_t conv_kernel;      /* 0 SIMT fp32, 1 tcgen05 3xTF32 (A in smem), 2 tcgen05 TF32, 3 tcgen05 3xTF32 (A in TMEM),
                                4 fully fused tcgen05 3xTF32 conv,
-                               5 fused conv with FP16 hi/lo MMAs + per-row scaling (default) */
+                               5 fused conv with FP16 hi/lo MMAs + per-row scaling (fp32-grade),
+                               6 mode 5 on CTA pairs (cta_group::2; bit-identical to 5; default),
+                               7 / 8 fp16 main product + two e4m3 cross-term MMAs (single CTA / CTA pairs; opt-in, ~5e-5 on scores),
+                               9 mode 5 with two gather/fold warpgroups (experiment) */
   int32_t reserved[7];
   const int32_t* atom14_group;  /* [21][14] restype_atom14_to_rigid_group (protein_constants.py:1177-1199) */
   /* sparse CG tables of the pseudo-torque product harmonics: triples (2,2,0), (1,2,1), (2,2,1) */
@@ -283,7 +286,9 @@ int b200dock_tp_kernel_time_ms(B200Handle* h, double* ms, int64_t* launches);
 #define B200_TAP_H_ATOM0 4
 #define B200_TAP_CONV_BUF 5   /* arg = conv*16 + which; which: 0 emb[E][48], 1 sh[E][9|8], 2 H1[E][160],
                                  3 Zt[tiles][z][128], 4 msg[E][168], 5 seg_ptr[T+1] (int32), 6 centre msg [N_l][12] */
-/* Debug knobs (tests only): key 0 = number of interaction layers to run (default 6). */
+/* Debug knobs (tests / tools only): key 0 = number of interaction layers to run (default 6); key 1 = wait-cycle accounting of the
+ * fused conv kernels on (1) / off (0): 148 CTAs x 32 int64 counters (slots 0..7 MMA-issuing warp, 8..15 one fold warp; only filled by a
+ * library built with -DB200DOCK_TRACE), read back with b200dock_debug_tap(what = 7). */
 int b200dock_debug_set(B200Handle* h, int key, int value);
 int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t cap_bytes, size_t* n_bytes);
 

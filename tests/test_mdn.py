@@ -175,3 +175,19 @@ def test_sampler_to_mdn_pipeline_matches_oracle_scorer():
     ref = oenc.karmadock_forward(ksd, x)
     assert scores.shape == (B,) and torch.isfinite(scores).all()
     assert torch.allclose(scores.cpu(), ref, rtol=2e-4, atol=1e-4), (scores.cpu(), ref)
+
+
+@pytest.mark.parametrize("tag", ["n36", "n20_small_k", "n105"])
+def test_protein_featuriser_matches_reference_function_body(tag):
+    """mdn_features.protein_features against the output of the reference's own get_protein_feature body
+    (scoring/dataset/protein_feature.py:137-217, run unmodified on a synthetic pocket; tools/make_golden_mdn.py) - the per-pose and the
+    batched variant."""
+    from diffbindfr_b200 import mdn_features
+    g = load_golden("mdn_protein_features.pt")[tag]
+    n = g["atom14"].shape[0]
+    dih = g["sincos"][:, :3].reshape(n, 6)
+    for f in (mdn_features.protein_features(g["atom14"], g["mask"], dih, g["topk"]),
+              mdn_features.protein_features_batched(g["atom14"][None], g["mask"], dih, g["topk"])):
+        assert torch.equal(f["edge_index"], g["edge_index"])
+        for k in ("node_s", "node_v", "edge_s", "edge_v"):
+            assert torch.allclose(f[k], g[k], rtol=0, atol=5e-7), k

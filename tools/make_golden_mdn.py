@@ -50,3 +50,45 @@ for tag, kw in (("small", dict(seed=1)), ("cfgA", dict(seed=2, n_lig=(30,) * 4, 
     print(tag, "O1 vs O2: pro", (pro_s - o_pro).abs().max().item(), "lig", (lig_s - o_lig).abs().max().item(), "score", (score - o_score).abs().max().item(), score)
     full[tag] = dict(kwargs=kw, pro_s=pro_s, lig_s=lig_s, score=score)
 torch.save(full, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "mdn_full.pt"))
+
+# ---- protein featuriser: the REFERENCE's get_protein_feature body (scoring/dataset/protein_feature.py:137-217) run unmodified on a
+#      synthetic pocket.  Only its parsing front end (openfold PDB parsing / atom37 transforms) is replaced by stubs that hand it the
+#      per-residue tensors it would have produced; torch_cluster.knn_graph is the restatement in diffbindfr_b200/mdn_features.py.
+import types
+import numpy as np
+from diffbindfr_b200 import mdn_features
+
+sys.modules["torch_cluster"].knn_graph = mdn_features.knn_graph
+for name in ("openfold", "openfold.np", "openfold.data", "openfold.data.data_transforms"):
+    if name not in sys.modules:
+        m = types.ModuleType(name); m.__path__ = []; sys.modules[name] = m
+sys.modules["openfold.np"].residue_constants = types.SimpleNamespace()
+sys.modules["openfold.np"].protein = types.SimpleNamespace(Protein=object, from_pdb_string=None)
+_ident = lambda d: d
+for fn in ("make_atom14_masks", "make_atom14_positions", "get_backbone_frames", "make_seq_mask"):
+    setattr(sys.modules["openfold.data.data_transforms"], fn, _ident)
+sys.modules["openfold.data.data_transforms"].squeeze_features = lambda d: {k: v.squeeze(0) for k, v in d.items()}
+sys.modules["openfold.data.data_transforms"].atom37_to_torsion_angles = lambda: _ident
+p = shims._ThinPackage("DiffBindFR.scoring.dataset"); p.__path__ = ["/root/reference/DiffBindFR/scoring/dataset"]; sys.modules["DiffBindFR.scoring.dataset"] = p
+pf = importlib.import_module("DiffBindFR.scoring.dataset.protein_feature")
+
+feat_fix = {}
+for tag, n_res, seed in (("n36", 36, 11), ("n20_small_k", 20, 12), ("n105", 105, 13)):
+    rng = np.random.default_rng(seed)
+    pk = synth.make_pocket(rng, n_res, 12.0 * max(n_res / 36.0, 1.0) ** (1.0 / 3.0))
+    a14 = pk["atom14_position"].astype(np.float32); m14 = pk["atom14_mask"].astype(np.float32)
+    ang = rng.uniform(-np.pi, np.pi, size=(n_res, 7)).astype(np.float32)
+    sincos = np.stack([np.sin(ang), np.cos(ang)], -1)
+    feats = dict(aatype=pk["sequence"].astype(np.int64), residue_index=np.arange(n_res), atom14_gt_positions=a14, atom14_atom_exists=m14,
+                 torsion_angles_sin_cos=sincos, alt_torsion_angles_sin_cos=sincos, torsion_angles_mask=np.ones((n_res, 7), np.float32),
+                 domain_name=np.array([b"x"], dtype=np.object_), sequence=np.array([b"x"], dtype=np.object_))
+    pf.protein.from_pdb_string = lambda s, _: None
+    pf.make_pdb_features = lambda obj, desc, is_distillation=False, _f=feats: dict(_f)
+    topk = 30 if tag != "n20_small_k" else 8
+    ca, xyz_full, seq, node_s, node_v, ei, edge_s, edge_v = pf.get_protein_feature("synthetic", topk=topk, pdb_string=True)
+    ours = mdn_features.protein_features(torch.from_numpy(a14), torch.from_numpy(m14), torch.from_numpy(sincos[:, :3]).reshape(n_res, 6), topk)
+    print(tag, "featuriser vs reference body:", *(f"{k} {float((ours[k].double() - v.double()).abs().max()):.1e}" for k, v in
+          (("node_s", node_s), ("node_v", node_v), ("edge_s", edge_s), ("edge_v", edge_v))), "edges equal:", bool(torch.equal(ours["edge_index"], ei)))
+    feat_fix[tag] = dict(atom14=torch.from_numpy(a14), mask=torch.from_numpy(m14), sincos=torch.from_numpy(sincos), topk=topk, node_s=node_s.float(),
+                         node_v=node_v.float(), edge_index=ei, edge_s=edge_s.float(), edge_v=edge_v.float(), seq=seq)
+torch.save(feat_fix, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "mdn_protein_features.pt"))

@@ -188,8 +188,18 @@ def main():
     from diffbindfr_b200 import batch as batch_mod
     from diffbindfr_b200.engine import Engine
 
-    # weak scaling: every rank owns one 40-pose batch (poses / complexes shard without any exchange)
-    b = synth.make_batch(**workload_kwargs(args.workload), seed=rank)
+    # weak scaling: every rank owns one 40-pose batch (poses / complexes shard without any exchange).  For the single-complex
+    # workloads all ranks dock the SAME complex (what sharding the -np pose list of one complex means): rank 0 holds exactly the
+    # N=1 batch, the other ranks hold 40 further random poses of it
+    kw = workload_kwargs(args.workload)
+    if rank == 0 or kw.get("n_complex", 1) != 1 or isinstance(kw.get("n_res"), (tuple, list)) or isinstance(kw.get("n_lig"), (tuple, list)):
+        b = synth.make_batch(**kw, seed=0 if kw.get("n_complex", 1) == 1 else rank)
+    else:
+        rng0 = np.random.default_rng(0)
+        rad = kw.get("radius", 12.0) * (kw["n_res"] / 36.0) ** (1.0 / 3.0)
+        base = synth.make_sample(rng0, kw["n_res"], kw["n_lig"], rad, kw.get("tr_sigma", 3.0))
+        rngr = np.random.default_rng(1000 + rank)
+        b = synth.collate([synth.repose(base, rngr, kw.get("tr_sigma", 3.0)) for _ in range(kw["n_poses"])])
     sd = weights.random_state_dict(0)
     eng = Engine(local, conv_kernel=args.conv_kernel)
     eng.load_state_dict(sd)
@@ -349,7 +359,7 @@ def main():
                        if args.workload == "cfgA" else f"{args.workload}: {workload_kwargs(args.workload)} per GPU",
                        "poses_per_gpu": int(b["num_graphs"]), "pocket_atoms": int(b["rec_atm_pos"].shape[0]),
                        "ligand_atoms": int(b["lig_pos"].shape[0]), "edges": counts, "conv_kernel": args.conv_kernel,
-                       "random_init_weights": True, "parallelism": f"pose-sharded x{world}, one final all_gather",
+                       "random_init_weights": True, "parallelism": f"pose-sharded x{world} (same complex, 40 different poses per rank), one final all_gather",
                        "l2": "no explicit flush: the per-step working set (per-edge H1/Z/message buffers "
                              f"~{(counts['lig'] + counts['atom'] + 2 * counts['cross']) * (160 + 624 + 168) * 4 / 1e9:.2f} GB + 101 MB weights) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,

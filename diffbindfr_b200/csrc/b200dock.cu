@@ -388,23 +388,32 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     if ((rc = build_graph<G_TOR>(h, G, h->cw[4], st))) return rc;
     edge_feat<G_TOR>(h, b, h->cw[4], edge_mlp(h, B200_W_TOR_EDGE, 0, 0), nullptr, 5.0f, st);
   }
-  for (int which = 0; which < 2; ++which) {
-    ConvWs& w = h->cw[4 + which];
-    if (which == 1) side_join(h, st);
-    if (w.T == 0) continue;
-    const float* tab = which == 0 ? hl : ha;
+  side_join(h, st);
+  {   // both pseudo-torque convs in ONE tensor-product launch (the ligand-torsion graph alone fills a quarter of the SMs)
     ConvLaunch L{};
     TcExtra X{};
-    L.n = 1; L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
-    L.c[0] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8, X, 0);
-    if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
-    if ((rc = launch_tp(h, L, X, st))) return rc;
-    TorHeadArgs T{};
-    T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
-    T.mlp = W + off[which == 0 ? B200_W_TOR_FINAL : B200_W_SC_FINAL];
-    T.norm2 = which == 0 ? c.tor_score_norm2 : c.sc_tor_score_norm2; T.out = which == 0 ? tor : sc;
-    k_tor_head<<<grid_for(w.T, 8, 148 * 8), 256, 0, st>>>(T);
-    h->launches += 1;
+    L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
+    for (int which = 0; which < 2; ++which) {
+      ConvWs& w = h->cw[4 + which];
+      if (w.T == 0) continue;
+      const float* tab = which == 0 ? hl : ha;
+      L.c[L.n] = conv_args(h, w, 24 + which, B200_PLAN_TOR, tab, tab, 1, which == 0 ? b.tor_bonds : b.sc_bonds, 8, X, L.n);
+      L.n += 1;
+    }
+    if (L.n) {
+      if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
+      if ((rc = launch_tp(h, L, X, st))) return rc;
+    }
+    for (int which = 0; which < 2; ++which) {
+      ConvWs& w = h->cw[4 + which];
+      if (w.T == 0) continue;
+      TorHeadArgs T{};
+      T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
+      T.mlp = W + off[which == 0 ? B200_W_TOR_FINAL : B200_W_SC_FINAL];
+      T.norm2 = which == 0 ? c.tor_score_norm2 : c.sc_tor_score_norm2; T.out = which == 0 ? tor : sc;
+      k_tor_head<<<grid_for(w.T, 8, 148 * 8), 256, 0, st>>>(T);
+      h->launches += 1;
+    }
   }
   CK(cudaGetLastError());
   return B200_OK;

@@ -132,3 +132,27 @@ def test_build_atom14_matches_synth_builder():
                                 b["rigid_group_positions"], b["torsion_angle"])
     m = b["atom14_mask"].bool()
     assert torch.allclose(a14[m], b["rec_atm_pos"], atol=2e-4)
+
+
+def test_operand_format_emulation_orders_the_modes():
+    """CPU emulation (tools/precision_study.py) of the tensor-core operand formats on the oracle's per-edge weight generator:
+    fp16 hi/lo x3 (modes 5/6) is fp32-grade, fp16 + two e4m3 cross terms (modes 7/8) stays inside the 2e-4 score bar, the
+    uncompensated fp16 product does not - the reason the kernels pay for the compensation MMAs."""
+    import importlib.util, os
+    spec_ = importlib.util.spec_from_file_location("precision_study", os.path.join(os.path.dirname(__file__), "..", "tools", "precision_study.py"))
+    ps = importlib.util.module_from_spec(spec_); spec_.loader.exec_module(ps)
+    g = load_golden("score_tiny.pt")
+    b = synth.make_batch(**g["workload"], seed=g["seed"])
+    d = dict(b); d.update(conditioning(b, **g["cond"]))
+    sd = weights.random_state_dict(0)
+    orig = omodel.mlp
+    err = {}
+    try:
+        for v in ("x3", "f8s", "hi"):
+            omodel.mlp = ps.patched_mlp(v, orig)
+            out = omodel.score_model(sd, d, torch.float32)
+            err[v] = max(((o - g[k]).abs().max() / g[k].abs().max().clamp_min(1e-3)).item() for k, o in zip(("tr", "rot", "tor", "sc"), out))
+    finally:
+        omodel.mlp = orig
+    assert err["x3"] < 1e-5 and err["f8s"] < 2e-4 and err["hi"] > 2e-4, err
+    assert err["x3"] < err["f8s"] < err["hi"]

@@ -100,3 +100,21 @@ def slice_noise(noise: Sequence[Dict[str, torch.Tensor]], graphs: Sequence[int],
     tor_idx = torch.cat([torch.arange(int(tor_off[i]), int(tor_off[i + 1])) for i in g.tolist()]) if len(g) else torch.zeros(0, dtype=torch.long)
     sc_idx = torch.cat([torch.arange(int(sc_off[i]), int(sc_off[i + 1])) for i in g.tolist()]) if len(g) else torch.zeros(0, dtype=torch.long)
     return [dict(tr=z["tr"][g], rot=z["rot"][g], tor=z["tor"][tor_idx], sc=z["sc"][sc_idx]) for z in noise]
+
+
+def regroup_results(model_out: Sequence[Tuple[torch.Tensor, torch.Tensor]], n_pairs: int, num_poses: int, batch_repeat: bool = False,
+                    pair_names: Optional[Sequence[str]] = None):
+    """Per-pair view of the flat sampler output, as ``DiffBindFR/common/engines.py:206-220`` builds it: ``model_out`` is the list
+    of ``(ligand (T, n_l, 3), atom14 (T, n_r, 14, 3))`` in dataset order - pair-major when ``batch_repeat`` (``num_poses`` consecutive
+    entries per pair), pose-major otherwise (``inference_dataset.py:480-490``; both ``predict.py:109`` and ``eval.py:108`` use
+    ``batch_repeat=False``).  Returns ``[(names, ligand (N_pose, T, n_l, 3), atom14 (N_pose, T, n_r, 14, 3))]`` per pair - the
+    ``(N_pose, N_traj, N_atom, 3)`` layout ``evaluation/export.py:106-312`` consumes, stacked once instead of zipped lists."""
+    assert n_pairs * num_poses == len(model_out), "number of results does not match n_pairs * num_poses"
+    names = list(pair_names) if pair_names is not None else [None] * len(model_out)
+    out = []
+    for p in range(n_pairs):
+        idx = [num_poses * p + k for k in range(num_poses)] if batch_repeat else [n_pairs * k + p for k in range(num_poses)]
+        lig = torch.stack([model_out[i][0] for i in idx])
+        a14 = torch.stack([model_out[i][1] for i in idx])
+        out.append((tuple(names[i] for i in idx), lig, a14))
+    return out

@@ -171,3 +171,26 @@ def test_slice_noise_matches_full_batch_layout():
                 assert torch.equal(z["tor"][t0:t0 + tor_n[gi]], full[s]["tor"][ft:ft + tor_n[gi]])
                 assert torch.equal(z["sc"][s0:s0 + sc_n[gi]], full[s]["sc"][fs:fs + sc_n[gi]])
                 t0 += tor_n[gi]; s0 += sc_n[gi]
+
+
+def test_regroup_results_matches_reference_slicing():
+    """Same grouping as the zip/slice code of DiffBindFR/common/engines.py:206-220, for both dataset orders."""
+    n_pairs, num_poses = 3, 4
+    nl, nr = [5, 7, 6], [8, 9, 4]
+    for batch_repeat in (False, True):
+        order = [(p, k) for p in range(n_pairs) for k in range(num_poses)] if batch_repeat else [(p, k) for k in range(num_poses) for p in range(n_pairs)]
+        model_out = [(torch.full((1, nl[p], 3), float(10 * p + k)), torch.full((1, nr[p], 14, 3), float(-(10 * p + k)))) for p, k in order]
+        names = [f"pair{p}" for p, k in order]
+        # the reference's own slicing, restated literally
+        if batch_repeat:
+            results = [model_out[num_poses * i: num_poses * (i + 1)] for i in range(n_pairs)]
+            pn = [names[num_poses * i: num_poses * (i + 1)] for i in range(n_pairs)]
+        else:
+            results = [model_out[n_pairs * i: n_pairs * (i + 1)] for i in range(num_poses)]
+            pn = [names[n_pairs * i: n_pairs * (i + 1)] for i in range(num_poses)]
+            results = list(zip(*results)); pn = list(zip(*pn))
+        got = shard.regroup_results(model_out, n_pairs, num_poses, batch_repeat, names)
+        for p in range(n_pairs):
+            assert tuple(pn[p]) == got[p][0] and got[p][1].shape == (num_poses, 1, nl[p], 3) and got[p][2].shape == (num_poses, 1, nr[p], 14, 3)
+            for k in range(num_poses):
+                assert torch.equal(got[p][1][k], results[p][k][0]) and torch.equal(got[p][2][k], results[p][k][1])

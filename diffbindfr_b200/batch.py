@@ -22,7 +22,7 @@ class CBatch(C.Structure):
             "tor_bonds", "tor_ptr", "rot_mask", "rot_mask_off",
             "pocket_feat", "rec_atm_pos", "atom_ptr", "atom_batch", "atom_slot", "res_ptr", "atom14_mask", "sequence",
             "backbone_transl", "backbone_rots", "default_frame", "rigid_group_pos", "torsion_angle", "sc_bonds",
-            "sc_index")]
+            "sc_index", "sc_ptr")]
 
 
 POINTER_FIELDS = [n for n, t in CBatch._fields_ if t is C.c_void_p]
@@ -73,6 +73,9 @@ def prepare(batch: Dict[str, object]) -> Dict[str, np.ndarray]:
     n_sc = sc_bonds.shape[0]
     sc_index = np.full(scm.shape, -1, dtype=np.int32)
     sc_index[scm] = np.arange(n_sc, dtype=np.int32)
+    sc_graph = ab[sc_bonds[:, 0]] if n_sc else np.zeros(0, dtype=np.int64)
+    assert n_sc == 0 or np.all(np.diff(sc_graph) >= 0), "chi bonds must be grouped by graph"
+    sc_ptr = np.concatenate([[0], np.cumsum(np.bincount(sc_graph, minlength=B))]).astype(np.int32)
     res_graph = ab[np.searchsorted(np.cumsum(amask.sum(1)), np.arange(N_r), side="right").clip(max=N_a - 1)] if N_a else np.zeros(N_r, np.int64)
     # residues without atoms inherit the graph of the next atom; res_ptr only used for bookkeeping
     res_ptr = np.concatenate([[0], np.cumsum(np.bincount(res_graph, minlength=B))]).astype(np.int32)
@@ -90,7 +93,7 @@ def prepare(batch: Dict[str, object]) -> Dict[str, np.ndarray]:
         default_frame=_np(batch["default_frame"], np.float32), rigid_group_pos=_np(batch["rigid_group_positions"], np.float32),
         torsion_angle=_np(batch["torsion_angle"], np.float32),
         sc_bonds=sc_bonds.astype(np.int32).reshape(-1, 2) if n_sc else np.zeros((1, 2), np.int32),
-        sc_index=sc_index)
+        sc_index=sc_index, sc_ptr=sc_ptr)
     out["dims"] = dict(B=B, N_l=N_l, N_a=N_a, N_r=N_r, E_b=E_b, n_tor=n_tor, n_sc=n_sc, max_lig_atoms=int(nl.max()),
                        rot_mask_bytes=int(pos), cross_pairs=int((nl * na).sum()), atom_pairs=int((na * na).sum()))
     return out

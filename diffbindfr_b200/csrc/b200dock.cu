@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -11,12 +12,9 @@
 #include "graph.cuh"
 #include "embed.cuh"
 #include "conv.cuh"
-#include "conv_tc.cuh"
+#include "tc_common.cuh"
 #include "conv_fused.cuh"
 #include "conv_fused2.cuh"
-#include "conv_fused8.cuh"
-#include "conv_fused8x2.cuh"
-#include "conv_fused_wg.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
 #include "mdn.cuh"
@@ -41,15 +39,19 @@ struct Buf {
 
 struct ConvWs {                 // per edge family: lig, atom, al, la, tor, sc
   int T = 0; int cap = 0; int z_max = 0;
-  Buf counts, seg, es, ed, eaux, emb, sh, H1, H1lo, Zt, msg;
+  Buf counts, seg, gpad, es, ed, eaux, emb, sh, H1, Zt, msg, agg, part;
 };
 
 struct ConvW {                  // views into the device weight blob
   const float *W1t, *b1, *W2p; LnParams ln;
-  const float *W2hi = nullptr, *W2lo = nullptr; int n_cols = 0;
-  const float *W1hi = nullptr, *W1lo = nullptr;
+  int n_cols = 0;
   const __half *W1h16 = nullptr, *W1l16 = nullptr, *W2h16 = nullptr, *W2l16 = nullptr; float inv_s1 = 1.f, inv_s2 = 1.f;
 };
+
+// conv kernels: 0 exact fp32 SIMT (192-column units), 5 fused tcgen05 single CTA, 6 fused tcgen05 CTA pairs + fused scatter (144)
+inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6; }
+inline int variant_of_kernel(int k) { return k == 0 ? 0 : 1; }
+inline bool kernel_keeps_msg(int k) { return k == 0 || k == 5; }
 
 }  // namespace
 
@@ -59,9 +61,10 @@ struct B200Handle {
   B200Config cfg;
   std::vector<std::vector<int32_t>> hold_i; std::vector<std::vector<float>> hold_f;
   DevPlan dplans[B200_N_PLANS];
+  int variant = 0;              // slot of c_plans this handle's plans live in
   std::vector<void*> plan_allocs;
   int* d_tor_cg_ijk = nullptr; float* d_tor_cg_val = nullptr;
-  float* d_blob = nullptr; float* d_w2split = nullptr; float* d_w1p = nullptr; __half* d_w16 = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
+  float* d_blob = nullptr; __half* d_w16 = nullptr; size_t blob_n = 0; std::vector<int64_t> off; bool weights = false;
   ConvW convw[26];
   // workspace
   ConvWs cw[6];
@@ -80,9 +83,9 @@ struct B200Handle {
   int n_sms = 148;
   int debug_layers = 6;
   int tp_grid = 148;
-  std::vector<float> cg_dense;
-  int dbg_flag = 0;
+  std::vector<float> cg_dense; int atom14_group[21 * 14];
   // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
+  int* host_meta = nullptr; bool deferred_check = false;
   Buf trace; bool trace_on = false;
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool use_side = true;
 };
@@ -135,21 +138,22 @@ int setup_workspace(B200Handle* h, const B200Batch& b) {
   caps[2] = caps[3] = b.cross_pairs;
   caps[4] = 32LL * b.n_tor;
   caps[5] = 32LL * b.n_sc;
+  for (int c = 0; c < 6; ++c) caps[c] += 32LL * b.B;          // every graph's edge range is padded to a multiple of 32 slots
   int Ts[6] = {b.N_l, b.N_a, b.N_l, b.N_a, b.n_tor, b.n_sc};
   int zmax[6] = {624, 624, 624, 624, 144, 144};
   for (int c = 0; c < 6; ++c) {
     ConvWs& w = h->cw[c];
     w.T = Ts[c]; w.cap = r128(caps[c]); w.z_max = zmax[c];
-    ENS(w.counts, (size_t)(w.T + 1) * 4); ENS(w.seg, (size_t)(w.T + 2) * 4);
+    ENS(w.counts, (size_t)(w.T + 1) * 4); ENS(w.seg, (size_t)(w.T + 2) * 4); ENS(w.gpad, (size_t)(b.B + 1) * 4);
     ENS(w.es, (size_t)w.cap * 4); ENS(w.ed, (size_t)w.cap * 4);
     if (c == 0) ENS(w.eaux, (size_t)w.cap * 4);
     ENS(w.emb, (size_t)w.cap * NSC * 4); ENS(w.sh, (size_t)w.cap * 9 * 4);
-    if (h->cfg.conv_kernel < 4) {
+    if (h->cfg.conv_kernel == 0) {
       ENS(w.H1, (size_t)w.cap * KP * 4);
-      if (h->cfg.conv_kernel == 1) ENS(w.H1lo, (size_t)w.cap * KP * 4);
       ENS(w.Zt, (size_t)w.cap * w.z_max * 4);
     }
-    ENS(w.msg, (size_t)w.cap * HS * 4);
+    if (kernel_keeps_msg(h->cfg.conv_kernel)) ENS(w.msg, (size_t)w.cap * HS * 4);
+    ENS(w.agg, (size_t)(w.T + 1) * HS * 4); ENS(w.part, (size_t)(w.cap / 32) * 2 * HS * 4);
   }
   for (int m = 0; m < 6; ++m) ENS(h->pre[m], (size_t)b.B * NSC * 4);
   ENS(h->h_lig, (size_t)b.N_l * HS * 4); ENS(h->h_atom, (size_t)b.N_a * HS * 4);
@@ -164,16 +168,6 @@ int setup_workspace(B200Handle* h, const B200Batch& b) {
   return B200_OK;
 }
 
-__global__ void k_split_tf32(const float* __restrict__ src, size_t n, float* __restrict__ hi, float* __restrict__ lo) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float v = src[i];
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    float h = __uint_as_float(hb);
-    hi[i] = h; lo[i] = v - h;
-  }
-}
-
 EdgeMlp edge_mlp(const B200Handle* h, int section, int n_bond, int n_sigma) {
   EdgeMlp m; m.w = h->d_blob + h->off[section]; m.n_bond = n_bond; m.n_sigma = n_sigma; return m;
 }
@@ -182,10 +176,11 @@ template <int KIND>
 int build_graph(B200Handle* h, const GraphArgs& G, ConvWs& w, cudaStream_t st) {
   if (w.T == 0) return B200_OK;
   k_graph_count<KIND><<<grid_for((long long)w.T * 32, 256, 148 * 8), 256, 0, st>>>(G, w.T, w.counts.as<int>());
-  k_scan<<<1, 1024, 0, st>>>(w.counts.as<int>(), w.T, w.seg.as<int>());
-  k_graph_fill<KIND><<<grid_for((long long)w.T * 32, 256, 148 * 8), 256, 0, st>>>(G, w.T, w.seg.as<int>(), w.cap - 128, w.es.as<int>(),
-                                                               w.ed.as<int>(), KIND == G_LIG ? w.eaux.as<int>() : nullptr,
-                                                               h->errflag.as<int>());
+  k_scan_aligned<KIND><<<1, 1024, 0, st>>>(G, w.T, w.cap - 128, w.counts.as<int>(), w.seg.as<int>(), w.gpad.as<int>(),
+                                           h->errflag.as<int>());
+  k_graph_fill<KIND><<<grid_for((long long)w.T * 32, 256, 148 * 8), 256, 0, st>>>(G, w.T, w.seg.as<int>(), w.counts.as<int>(), w.cap,
+                                                               w.es.as<int>(), w.ed.as<int>(),
+                                                               KIND == G_LIG ? w.eaux.as<int>() : nullptr);
   h->launches += 3;
   return B200_OK;
 }
@@ -210,63 +205,72 @@ void edge_feat(B200Handle* h, const B200Batch& b, ConvWs& w, EdgeMlp mlp, const 
   h->launches += 1;
 }
 
-int launch_tp(B200Handle* h, const ConvLaunch& L, const TcExtra& X, cudaStream_t st) {
+int launch_tp(B200Handle* h, const ConvLaunch& L, const Fused16Extra& F, cudaStream_t st) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
-  if (h->cfg.conv_kernel >= 5) {
-    Fused16Extra F{};
-    for (int i = 0; i < L.n; ++i) {
-      F.W1hi[i] = X.W1h16[i]; F.W1lo[i] = X.W1l16[i]; F.W2hi[i] = X.W2h16[i]; F.W2lo[i] = X.W2l16[i];
-      F.w2_rows[i] = X.w2_rows[i] + 144;
-    }
-    rc = h->cfg.conv_kernel == 9 ? launch_conv_fused16wg(L, F, h->tp_grid, st) : h->cfg.conv_kernel == 8 ? launch_conv_fused8x2(L, F, h->tp_grid, st) : h->cfg.conv_kernel == 7 ? launch_conv_fused8(L, F, h->tp_grid, st)
-       : h->cfg.conv_kernel == 6 ? launch_conv_fused16x2(L, F, h->tp_grid, st) : launch_conv_fused16(L, F, h->tp_grid, st);
-  } else if (h->cfg.conv_kernel == 4) {
-    FusedExtra F{};
-    for (int i = 0; i < L.n; ++i) { F.W1hi[i] = X.W1hi[i]; F.W1lo[i] = X.W1lo[i]; F.W2lo[i] = X.W2_lo[i]; F.w2_rows[i] = X.w2_rows[i]; }
-    rc = launch_conv_fused(L, F, h->tp_grid, st);
-  } else if (h->cfg.conv_kernel == 0) {
+  const int k = h->cfg.conv_kernel;
+  if (k == 6) rc = launch_conv_fused16x2(L, F, h->tp_grid, st);
+  else if (k == 5) rc = launch_conv_fused16(L, F, h->tp_grid, st);
+  else {
+    k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
     k_conv_tp_simt<<<h->n_sms, TP_THREADS, TP_SMEM, st>>>(L);
-  } else {
-    rc = launch_conv_tc(L, X, h->cfg.conv_kernel, h->tp_grid, st);
+    h->launches += 1;
+  }
+  h->launches += 1;
+  if (kernel_keeps_msg(k)) {      // per-edge messages -> per-node sums (the CTA-pair kernel does this in its epilogue)
+    MsgScatterLaunch M{};
+    M.n = L.n;
+    for (int i = 0; i < L.n; ++i) {
+      const ConvArgs& C = L.c[i];
+      M.c[i] = MsgScatterArgs{C.n_edges, C.es, C.seg, C.counts, C.msg, C.agg, C.part, h->dplans[C.cgp].out_dim};
+    }
+    k_msg_scatter<<<h->n_sms * 4, 256, 0, st>>>(M);
+    h->launches += 1;
   }
   if (h->profiling) { cudaEventRecord(e1, st); h->tp_events.push_back({e0, e1}); }
-  h->launches += 1;
   if (rc) { char m[64]; snprintf(m, sizeof m, "tcgen05 conv launch failed (%d)", rc); FAIL(B200_ERR_CUDA, m); }
   return B200_OK;
 }
 
 ConvArgs conv_args(B200Handle* h, ConvWs& w, int widx, int plan, const float* tabA, const float* tabB, int mode,
-                   const int* bonds, int sh_stride, TcExtra& X, int slot) {
+                   const int* bonds, int sh_stride, Fused16Extra& X, int slot) {
   ConvArgs C{};
-  X.H1_lo[slot] = w.H1lo.as<float>(); X.W2_lo[slot] = h->convw[widx].W2lo;
-  X.W1hi[slot] = h->convw[widx].W1hi; X.W1lo[slot] = h->convw[widx].W1lo;
-  X.W1h16[slot] = h->convw[widx].W1h16; X.W1l16[slot] = h->convw[widx].W1l16;
-  X.W2h16[slot] = h->convw[widx].W2h16; X.W2l16[slot] = h->convw[widx].W2l16;
-  X.h1_rows[slot] = (uint64_t)w.cap; X.w2_rows[slot] = (uint64_t)h->convw[widx].n_cols;
+  const ConvW& cw = h->convw[widx];
+  X.W1hi[slot] = cw.W1h16; X.W1lo[slot] = cw.W1l16; X.W2hi[slot] = cw.W2h16; X.W2lo[slot] = cw.W2l16;
+  X.w2_rows[slot] = (uint64_t)cw.n_cols + 144;
   C.n_edges = w.seg.as<int>() + w.T; C.es = w.es.as<int>(); C.ed = w.ed.as<int>();
   C.emb = w.emb.as<float>(); C.sh = w.sh.as<float>(); C.sh_stride = sh_stride;
-  C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode; C.plan = plan;
-  C.W1t = h->convw[widx].W1t; C.b1 = h->convw[widx].b1;
-  C.W2p = (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3 || h->cfg.conv_kernel == 4) ? h->convw[widx].W2hi : h->convw[widx].W2p;
-  C.inv_s1 = h->convw[widx].inv_s1; C.inv_s2 = h->convw[widx].inv_s2;
-  C.H1 = w.H1.as<float>(); C.H1_lo = (h->cfg.conv_kernel == 1) ? w.H1lo.as<float>() : nullptr;
-  C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
+  C.tabA = tabA; C.tabB = tabB; C.bonds = bonds; C.mode = mode;
+  C.plan = h->variant * B200_N_PLANS + plan; C.cgp = plan;
+  C.W1t = cw.W1t; C.b1 = cw.b1; C.W2p = cw.W2p;
+  C.inv_s1 = cw.inv_s1; C.inv_s2 = cw.inv_s2;
+  C.H1 = w.H1.as<float>(); C.Zt = w.Zt.as<float>(); C.msg = w.msg.as<float>();
+  C.seg = w.seg.as<int>(); C.counts = w.counts.as<int>(); C.agg = w.agg.as<float>(); C.part = w.part.as<float>();
   return C;
 }
 
-// One evaluation of the score network on device-resident batch + conditioning.
-// The conv plans live in __constant__ memory (one copy per device and module); a handle re-uploads its own
-// tables, stream-ordered, whenever another handle used the device last.
-static B200Handle* g_plan_owner[64] = {nullptr};
+AggSrc agg_src(const ConvWs& w) { return AggSrc{w.seg.as<int>(), w.counts.as<int>(), w.agg.as<float>(), w.part.as<float>()}; }
 
-int bind_plans(B200Handle* h, cudaStream_t st) {
+// The conv plans live in __constant__ memory, one slot per unit-width variant and device; a slot's content is a pure function of
+// the static network spec, so it is written once (first handle of that variant on the device) and never changes afterwards:
+// handles with different conv kernels, on any stream or thread, cannot disturb each other's in-flight kernels.
+static std::mutex g_plan_mutex;
+static bool g_plan_done[64][B200_PLAN_VARIANTS] = {};
+static bool g_cg_done[64] = {};
+
+int bind_plans(B200Handle* h) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
   const int dev = h->device & 63;
-  if (g_plan_owner[dev] == h) return B200_OK;
-  CK(cudaMemcpyToSymbolAsync(c_plans, h->dplans, sizeof(DevPlan) * B200_N_PLANS, 0, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyToSymbolAsync(c_cg_dense, h->cg_dense.data(), h->cg_dense.size() * sizeof(float), 0, cudaMemcpyHostToDevice, st));
-  g_plan_owner[dev] = h;
+  if (!g_plan_done[dev][h->variant]) {
+    CK(cudaMemcpyToSymbol(c_plans, h->dplans, sizeof(DevPlan) * B200_N_PLANS, sizeof(DevPlan) * B200_N_PLANS * h->variant));
+    g_plan_done[dev][h->variant] = true;
+  }
+  if (!g_cg_done[dev]) {
+    CK(cudaMemcpyToSymbol(c_cg_dense, h->cg_dense.data(), h->cg_dense.size() * sizeof(float)));
+    CK(cudaMemcpyToSymbol(c_atom14_group, h->atom14_group, sizeof(int) * 21 * 14));
+    g_cg_done[dev] = true;
+  }
   return B200_OK;
 }
 
@@ -286,7 +290,6 @@ static inline void side_join(B200Handle* h, cudaStream_t st) {
 int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr, float* rot, float* tor, float* sc,
                  cudaStream_t st) {
   if (!h->weights) FAIL(B200_ERR_STATE, "weights not loaded");
-  { int rcb = bind_plans(h, st); if (rcb) return rcb; }
   const float* W = h->d_blob;
   const std::vector<int64_t>& off = h->off;
   // ---- sigma pre-activations
@@ -318,6 +321,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
   G.pocket_feat = b.pocket_feat; G.tr_sigma = c.tr_sigma;
   G.bond_ptr = b.bond_ptr; G.bond_dst = b.bond_dst; G.bond_eid = b.bond_eid;
   G.tor_bonds = b.tor_bonds; G.n_tor = b.n_tor; G.sc_bonds = b.sc_bonds; G.n_sc = b.n_sc;
+  G.tor_ptr = b.tor_ptr; G.sc_ptr = b.sc_ptr; G.B = b.B;
   G.lig_jmax = h->jmax_lig.as<int>(); G.atom_jmax = h->jmax_atom.as<int>();
   k_radius_cap<<<grid_for(b.N_l, 128, 148 * 8), 128, 0, st>>>(b.lig_pos, b.lig_batch, b.lig_ptr, b.N_l, 25.0f, 33, h->jmax_lig.as<int>());
   k_radius_cap<<<grid_for(b.N_a, 128, 148 * 8), 128, 0, s2>>>(b.rec_atm_pos, b.atom_batch, b.atom_ptr, b.N_a, 16.0f, 1001, h->jmax_atom.as<int>());
@@ -339,25 +343,24 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
   for (int l = 0; l < h->debug_layers; ++l) {
     const int plan = plan_of_layer(l);
     ConvLaunch L{};
-    TcExtra X{};
-    L.n = 4; L.dbg = h->dbg_flag; L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
+    Fused16Extra X{};
+    L.n = 4; L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
     L.c[0] = conv_args(h, h->cw[0], 0 * 6 + l, plan, hl, hl, 0, nullptr, 9, X, 0);     // lig
     L.c[1] = conv_args(h, h->cw[1], 1 * 6 + l, plan, ha, ha, 0, nullptr, 9, X, 1);     // atom
     L.c[2] = conv_args(h, h->cw[2], 2 * 6 + l, plan, hl, ha, 0, nullptr, 9, X, 2);     // al: target lig, gather atom
     L.c[3] = conv_args(h, h->cw[3], 3 * 6 + l, plan, ha, hl, 0, nullptr, 9, X, 3);     // la: target atom, gather lig
-    if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
     if ((rc = launch_tp(h, L, X, st))) return rc;
     NodeUpdateArgs U{};
-    U.plan = plan;
+    U.plan = h->variant * B200_N_PLANS + plan;
     U.N = b.N_l; U.h = hl;
-    U.seg[0] = h->cw[0].seg.as<int>(); U.msg[0] = h->cw[0].msg.as<float>(); U.ln[0] = h->convw[0 * 6 + l].ln;
-    U.seg[1] = h->cw[2].seg.as<int>(); U.msg[1] = h->cw[2].msg.as<float>(); U.ln[1] = h->convw[2 * 6 + l].ln;
+    U.src[0] = agg_src(h->cw[0]); U.ln[0] = h->convw[0 * 6 + l].ln;
+    U.src[1] = agg_src(h->cw[2]); U.ln[1] = h->convw[2 * 6 + l].ln;
     cudaStream_t s2 = side_fork(h, st);                                  // ligand and pocket node updates are independent
-    k_node_update<4><<<grid_for(b.N_l, 2, 148 * 16), 256, 0, st>>>(U);   // long segments: 4 warps per ligand atom
+    k_node_update<<<grid_for(b.N_l, 8, 148 * 8), 256, 0, st>>>(U);
     U.N = b.N_a; U.h = ha;
-    U.seg[0] = h->cw[1].seg.as<int>(); U.msg[0] = h->cw[1].msg.as<float>(); U.ln[0] = h->convw[1 * 6 + l].ln;
-    U.seg[1] = h->cw[3].seg.as<int>(); U.msg[1] = h->cw[3].msg.as<float>(); U.ln[1] = h->convw[3 * 6 + l].ln;
-    k_node_update<1><<<grid_for(b.N_a, 8, 148 * 8), 256, 0, s2>>>(U);
+    U.src[0] = agg_src(h->cw[1]); U.ln[0] = h->convw[1 * 6 + l].ln;
+    U.src[1] = agg_src(h->cw[3]); U.ln[1] = h->convw[3 * 6 + l].ln;
+    k_node_update<<<grid_for(b.N_a, 8, 148 * 8), 256, 0, s2>>>(U);
     side_join(h, st);
     h->launches += 2;
   }
@@ -368,7 +371,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     CenterArgs A{};
     A.lig_pos = b.lig_pos; A.lig_batch = b.lig_batch; A.N_l = b.N_l; A.centre = h->centre.as<float>();
     A.pre = h->pre[5].as<float>(); A.mlp = edge_mlp(h, B200_W_CENTER_EDGE, 0, 32); A.fc = W + off[B200_W_FINAL_FC];
-    A.h_lig = hl; A.cmsg = h->cmsg.as<float>();
+    A.h_lig = hl; A.cmsg = h->cmsg.as<float>(); A.plan = h->variant * B200_N_PLANS + B200_PLAN_FINAL;
     k_center_edge<<<b.N_l, 128, 0, s3>>>(A);
     CenterHeadArgs H{};
     H.cmsg = h->cmsg.as<float>(); H.lig_ptr = b.lig_ptr; H.B = b.B; H.ln = W + off[B200_W_FINAL_LN];
@@ -391,7 +394,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
   side_join(h, st);
   {   // both pseudo-torque convs in ONE tensor-product launch (the ligand-torsion graph alone fills a quarter of the SMs)
     ConvLaunch L{};
-    TcExtra X{};
+    Fused16Extra X{};
     L.trace = h->trace_on ? h->trace.as<long long>() : nullptr;
     for (int which = 0; which < 2; ++which) {
       ConvWs& w = h->cw[4 + which];
@@ -401,14 +404,13 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
       L.n += 1;
     }
     if (L.n) {
-      if (h->cfg.conv_kernel < 4) { k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L); h->launches += 1; }
       if ((rc = launch_tp(h, L, X, st))) return rc;
     }
     for (int which = 0; which < 2; ++which) {
       ConvWs& w = h->cw[4 + which];
       if (w.T == 0) continue;
       TorHeadArgs T{};
-      T.n = w.T; T.seg = w.seg.as<int>(); T.msg = w.msg.as<float>(); T.ln = h->convw[24 + which].ln;
+      T.n = w.T; T.plan = h->variant * B200_N_PLANS + B200_PLAN_TOR; T.src = agg_src(w); T.ln = h->convw[24 + which].ln;
       T.mlp = W + off[which == 0 ? B200_W_TOR_FINAL : B200_W_SC_FINAL];
       T.norm2 = which == 0 ? c.tor_score_norm2 : c.sc_tor_score_norm2; T.out = which == 0 ? tor : sc;
       k_tor_head<<<grid_for(w.T, 8, 148 * 8), 256, 0, st>>>(T);
@@ -428,22 +430,25 @@ __global__ void k_fill_cond(int B, int n_tor, int n_sc, const float* __restrict_
   if (i < n_sc) c_scn[i] = s.sc_tor_score_norm2;
 }
 
+// End-of-call check: ONE stream synchronisation that brings back the capacity flag and the edge counts of the last evaluation
+// (six 4-byte copies into a pinned block).  Skipped in deferred mode (b200dock_set_deferred_check): the call then returns with
+// all work merely enqueued and the caller runs b200dock_check when it needs the verdict.
 int check_errflag(B200Handle* h, cudaStream_t st) {
-  int flag = 0;
-  CK(cudaMemcpyAsync(&flag, h->errflag.p, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (flag) {
-    char msg[128];
-    snprintf(msg, sizeof msg, "edge list of graph kind %d overflowed its workspace capacity", flag - 1);
-    FAIL(B200_ERR_CAPACITY, msg);
-  }
-  int64_t* lc = h->last_counts;
-  int idx[5] = {0, 1, 2, 4, 5};
+  if (!h->host_meta) CK(cudaMallocHost((void**)&h->host_meta, 8 * sizeof(int)));
+  int* m = h->host_meta;
+  for (int i = 0; i < 8; ++i) m[i] = 0;
+  CK(cudaMemcpyAsync(&m[0], h->errflag.p, 4, cudaMemcpyDeviceToHost, st));
+  const int idx[5] = {0, 1, 2, 4, 5};
   for (int i = 0; i < 5; ++i) {
     ConvWs& w = h->cw[idx[i]];
-    int v = 0;
-    if (w.T > 0) CK(cudaMemcpy(&v, w.seg.as<int>() + w.T, 4, cudaMemcpyDeviceToHost));
-    lc[i] = v;
+    if (w.T > 0) CK(cudaMemcpyAsync(&m[1 + i], w.seg.as<int>() + w.T + 1, 4, cudaMemcpyDeviceToHost, st));   // real edges (slots incl. padding at [T])
+  }
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < 5; ++i) h->last_counts[i] = m[1 + i];
+  if (m[0]) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "edge list of graph kind %d overflowed its workspace capacity", m[0] - 1);
+    FAIL(B200_ERR_CAPACITY, msg);
   }
   return B200_OK;
 }
@@ -505,12 +510,13 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   *out = h;
   h->device = device;
   h->cfg = *cfg;
+  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs)");
+  h->variant = variant_of_kernel(cfg->conv_kernel);
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->n_sms = prop.multiProcessorCount;
   h->tp_grid = h->n_sms;
-  if (const char* g = getenv("B200DOCK_DBG")) h->dbg_flag = atoi(g);
   if (const char* g = getenv("B200DOCK_NO_SIDE")) h->use_side = atoi(g) == 0;
   CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -525,18 +531,9 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
     d.in_dim = s.in_dim; d.sh_dim = s.sh_dim; d.out_dim = s.out_dim; d.z_numel = s.z_numel; d.n_cols = s.n_cols;
     d.n_blocks = s.n_blocks;
     for (int i = 0; i < B200_MAX_BLOCKS; ++i) d.blocks[i] = s.blocks[i];
-    d.n_cg = s.n_cg; d.n_chunks = s.n_chunks;
-    int rc;
-    int* ijk; float* val;
+    d.n_chunks = s.n_chunks;
     if (s.n_chunks > B200_MAX_CHUNKS) FAIL(B200_ERR_INVALID, "too many weight chunks in a conv plan");
-    if ((rc = upload(h, s.cg_ijk, (size_t)s.n_cg, &ijk))) return rc;
-    if ((rc = upload(h, s.cg_val, (size_t)s.n_cg, &val))) return rc;
-    d.cg_ijk = ijk; d.cg_val = val;
     for (int i = 0; i < s.n_chunks; ++i) { d.chunk_col[i] = s.chunk_col[i]; d.chunk_n[i] = s.chunk_n[i]; d.chunk_path[i] = s.chunk_path[i]; }
-    // keep host copies for the tensor-core path (chunk tables are read on the host too)
-    h->hold_i.emplace_back(s.chunk_col, s.chunk_col + s.n_chunks);
-    h->hold_i.emplace_back(s.chunk_n, s.chunk_n + s.n_chunks);
-    h->hold_i.emplace_back(s.chunk_path, s.chunk_path + s.n_chunks);
   }
   {
     std::vector<float>& dense = h->cg_dense;
@@ -553,13 +550,14 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
       }
     }
   }
-  CK(cudaMemcpyToSymbol(c_atom14_group, cfg->atom14_group, sizeof(int) * 21 * 14));
+  memcpy(h->atom14_group, cfg->atom14_group, sizeof(int) * 21 * 14);
   int rc;
+  if ((rc = bind_plans(h))) return rc;
   if ((rc = upload(h, cfg->tor_cg_ijk, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_ijk))) return rc;
   if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
   CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
   CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
-  if (conv_tc_init() || conv_fused_init() || conv_fused2_init() || conv_fused8_init() || conv_fused8x2_init() || conv_fused_wg_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  if (tc_init() || conv_fused_init() || conv_fused2_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
   h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
   return B200_OK;
 }
@@ -567,9 +565,8 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
 void b200dock_destroy(B200Handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (g_plan_owner[h->device & 63] == h) g_plan_owner[h->device & 63] = nullptr;
   auto fr = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; };
-  for (auto& w : h->cw) { fr(w.counts); fr(w.seg); fr(w.es); fr(w.ed); fr(w.eaux); fr(w.emb); fr(w.sh); fr(w.H1); fr(w.H1lo); fr(w.Zt); fr(w.msg); }
+  for (auto& w : h->cw) { fr(w.counts); fr(w.seg); fr(w.gpad); fr(w.es); fr(w.ed); fr(w.eaux); fr(w.emb); fr(w.sh); fr(w.H1); fr(w.Zt); fr(w.msg); fr(w.agg); fr(w.part); }
   for (auto& b : h->pre) fr(b);
   Buf* all[] = {&h->h_lig, &h->h_atom, &h->jmax_lig, &h->jmax_atom, &h->centre, &h->cmsg, &h->s_tr, &h->s_rot, &h->s_tor,
                 &h->s_sc, &h->atom14, &h->errflag, &h->c_temb, &h->c_trs, &h->c_rotn, &h->c_torn, &h->c_scn,
@@ -577,10 +574,9 @@ void b200dock_destroy(B200Handle* h) {
   for (Buf* b : all) fr(*b);
   if (h->pinned_in.p) cudaFreeHost(h->pinned_in.p);
   if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
+  if (h->host_meta) cudaFreeHost(h->host_meta);
   for (void* p : h->plan_allocs) cudaFree(p);
   if (h->d_blob) cudaFree(h->d_blob);
-  if (h->d_w2split) cudaFree(h->d_w2split);
-  if (h->d_w1p) cudaFree(h->d_w1p);
   if (h->d_w16) cudaFree(h->d_w16);
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -615,32 +611,6 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
     if (((uintptr_t)w.W2p & 15) != 0) FAIL(B200_ERR_INVALID, "conv record is not 16-byte aligned");
     w.n_cols = P.n_cols;
   }
-  if (h->cfg.conv_kernel == 1 || h->cfg.conv_kernel == 3 || h->cfg.conv_kernel == 4) {   // hi/lo TF32 split copies of every packed W2 for the 3xTF32 mode
-    size_t tot = 0;
-    for (int i = 0; i < 26; ++i) tot += (size_t)h->convw[i].n_cols * KP;
-    if (h->d_w2split) CK(cudaFree(h->d_w2split));
-    CK(cudaMalloc((void**)&h->d_w2split, 2 * tot * sizeof(float) + 1024));
-    size_t pos = 0;
-    for (int i = 0; i < 26; ++i) {
-      size_t n = (size_t)h->convw[i].n_cols * KP;
-      float* hi = h->d_w2split + pos; float* lo = h->d_w2split + tot + pos;
-      k_split_tf32<<<148 * 4, 256>>>(h->convw[i].W2p, n, hi, lo);
-      h->convw[i].W2hi = hi; h->convw[i].W2lo = lo;
-      pos += n;
-    }
-    CK(cudaDeviceSynchronize());
-  }
-  if (h->cfg.conv_kernel == 4) {   // first FC layer packed K-major with the bias column, TF32 hi/lo
-    const size_t n1 = (size_t)192 * KP;
-    if (h->d_w1p) CK(cudaFree(h->d_w1p));
-    CK(cudaMalloc((void**)&h->d_w1p, 26 * 2 * n1 * sizeof(float) + 1024));
-    for (int i = 0; i < 26; ++i) {
-      float* hi = h->d_w1p + (size_t)i * 2 * n1; float* lo = hi + n1;
-      k_build_w1p<<<120, 256>>>(h->convw[i].W1t, h->convw[i].b1, hi, lo);
-      h->convw[i].W1hi = hi; h->convw[i].W1lo = lo;
-    }
-    CK(cudaDeviceSynchronize());
-  }
   if (h->cfg.conv_kernel >= 5) {   // fp16 hi/lo copies of W1p / W2p with exact power-of-two scales
     size_t tot = 0;
     for (int i = 0; i < 26; ++i) tot += ((size_t)h->convw[i].n_cols + 144 + 192) * KH;
@@ -663,14 +633,8 @@ int b200dock_load_weights(B200Handle* h, const float* blob, size_t n, const int6
       const float s1 = scale_of(mx[0]), s2 = scale_of(mx[1]);
       __half* h1 = h->d_w16 + pos; __half* l1 = h1 + (size_t)192 * KH;
       __half* h2 = l1 + (size_t)192 * KH; __half* l2 = h2 + r2 * KH;
-      if (h->cfg.conv_kernel == 7 || h->cfg.conv_kernel == 8) {   // fp16 hi + e4m3 cross-term copies (the e4m3 pair takes the place of the fp16 lo array)
-        uint8_t* q1 = reinterpret_cast<uint8_t*>(l1); uint8_t* q2 = reinterpret_cast<uint8_t*>(l2);
-        k_build_w8<<<148, 256>>>(tmp, 192, 192, s1, h1, q1, q1 + (size_t)192 * KH);
-        k_build_w8<<<148 * 4, 256>>>(w.W2p, w.n_cols, (int)r2, s2, h2, q2, q2 + r2 * KH);
-      } else {
-        k_build_w16<<<148, 256>>>(tmp, 192, 192, s1, h1, l1);
-        k_build_w16<<<148 * 4, 256>>>(w.W2p, w.n_cols, (int)r2, s2, h2, l2);
-      }
+      k_build_w16<<<148, 256>>>(tmp, 192, 192, s1, h1, l1);
+      k_build_w16<<<148 * 4, 256>>>(w.W2p, w.n_cols, (int)r2, s2, h2, l2);
       w.W1h16 = h1; w.W1l16 = l1; w.W2h16 = h2; w.W2l16 = l2; w.inv_s1 = 1.0f / s1; w.inv_s2 = 1.0f / s2;
       pos += 2 * (size_t)192 * KH + 2 * r2 * KH;
     }
@@ -693,7 +657,7 @@ int b200dock_score(B200Handle* h, const B200Batch* batch, const B200Cond* cond, 
   rc = score_device(h, *batch, *cond, tr, rot, tor ? tor : h->s_tor.as<float>(), sc ? sc : h->s_sc.as<float>(), st);
   if (rc) return rc;
   h->last_batch = *batch; h->have_last = true;
-  return check_errflag(h, st);
+  return h->deferred_check ? B200_OK : check_errflag(h, st);
 }
 
 int b200dock_sample(B200Handle* h, B200Batch* batch, const B200Step* steps, int n_steps, const float* time_emb,
@@ -704,7 +668,20 @@ int b200dock_sample(B200Handle* h, B200Batch* batch, const B200Step* steps, int 
   h->launches = 0;
   int rc = sample_device(h, *batch, steps, n_steps, time_emb, noise, lig_traj, atom14_out, atom14_traj, st);
   if (rc) return rc;
-  return check_errflag(h, st);
+  return h->deferred_check ? B200_OK : check_errflag(h, st);
+}
+
+int b200dock_set_deferred_check(B200Handle* h, int on) {
+  if (!h) return B200_ERR_INVALID;
+  h->deferred_check = on != 0;
+  return B200_OK;
+}
+
+int b200dock_check(B200Handle* h, void* stream) {
+  if (!h) return B200_ERR_INVALID;
+  if (!h->errflag.p) return B200_OK;
+  CK(cudaSetDevice(h->device));
+  return check_errflag(h, (cudaStream_t)stream);
 }
 
 int b200dock_sample_host(B200Handle* h, const B200Batch* hb, const B200Step* steps, int n_steps, const float* time_emb,
@@ -734,7 +711,7 @@ int b200dock_sample_host(B200Handle* h, const B200Batch* hb, const B200Step* ste
          o_bt = add(b.backbone_transl, (size_t)b.N_r * 12), o_bR = add(b.backbone_rots, (size_t)b.N_r * 36),
          o_df = add(b.default_frame, (size_t)b.N_r * 8 * 64), o_rg = add(b.rigid_group_pos, (size_t)b.N_r * 14 * 12),
          o_ta = add(b.torsion_angle, (size_t)b.N_r * 20), o_scb = add(b.sc_bonds, (size_t)b.n_sc * 8),
-         o_sci = add(b.sc_index, (size_t)b.N_r * 16), o_noise = add(noise, nstride * n_steps * 4);
+         o_sci = add(b.sc_index, (size_t)b.N_r * 16), o_scp = add(b.sc_ptr, (size_t)(b.B + 1) * 4), o_noise = add(noise, nstride * n_steps * 4);
   if (total > h->pinned_in.cap) {
     if (h->pinned_in.p) CK(cudaFreeHost(h->pinned_in.p));
     h->pinned_in.p = nullptr; h->pinned_in.cap = 0;
@@ -758,7 +735,7 @@ int b200dock_sample_host(B200Handle* h, const B200Batch* hb, const B200Step* ste
   db.res_ptr = (const int*)(d + o_rptr); db.atom14_mask = (const uint8_t*)(d + o_m14); db.sequence = (const int*)(d + o_seq);
   db.backbone_transl = (const float*)(d + o_bt); db.backbone_rots = (const float*)(d + o_bR);
   db.default_frame = (const float*)(d + o_df); db.rigid_group_pos = (const float*)(d + o_rg);
-  db.torsion_angle = (float*)(d + o_ta); db.sc_bonds = (const int*)(d + o_scb); db.sc_index = (const int*)(d + o_sci);
+  db.torsion_angle = (float*)(d + o_ta); db.sc_bonds = (const int*)(d + o_scb); db.sc_index = (const int*)(d + o_sci); db.sc_ptr = (const int*)(d + o_scp);
   ENS(h->dev_a14_out, (size_t)b.N_r * 42 * 4);
   int rc = sample_device(h, db, steps, n_steps, time_emb, (const float*)(d + o_noise), nullptr,
                          h->dev_a14_out.as<float>(), nullptr, st);
@@ -998,8 +975,9 @@ int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t 
     std::vector<int> s(E), d(E);
     if (E) { CK(cudaMemcpy(s.data(), w.es.p, (size_t)E * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(d.data(), w.ed.p, (size_t)E * 4, cudaMemcpyDeviceToHost)); }
     int* o = (int*)host_out;
-    for (int i = 0; i < E; ++i) { o[2 * i] = s[i]; o[2 * i + 1] = d[i]; }
-    *n_bytes = bytes;
+    size_t n_real = 0;
+    for (int i = 0; i < E; ++i) if (s[i] >= 0) { o[2 * n_real] = s[i]; o[2 * n_real + 1] = d[i]; ++n_real; }   // es = -1: alignment padding
+    *n_bytes = n_real * 8;
     return B200_OK;
   } else if (what == B200_TAP_CONV_BUF) {
     int conv = arg / 16, which = arg % 16;
@@ -1010,10 +988,12 @@ int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t 
     size_t Ep = (size_t)((E + 127) / 128) * 128;
     if (which == 0) { src = w.emb.p; bytes = (size_t)E * NSC * 4; }
     else if (which == 1) { src = w.sh.p; bytes = (size_t)E * (conv >= 4 ? 8 : 9) * 4; }
-    else if (which == 2) { src = w.H1.p; bytes = Ep * KP * 4; }
-    else if (which == 3) { src = w.Zt.p; bytes = Ep * w.z_max * 4; }
-    else if (which == 4) { src = w.msg.p; bytes = Ep * HS * 4; }
-    else if (which == 5) { src = w.seg.p; bytes = (size_t)(w.T + 1) * 4; }
+    else if (which == 2 && w.H1.p) { src = w.H1.p; bytes = Ep * KP * 4; }
+    else if (which == 3 && w.Zt.p) { src = w.Zt.p; bytes = Ep * w.z_max * 4; }
+    else if (which == 4 && w.msg.p) { src = w.msg.p; bytes = Ep * HS * 4; }
+    else if (which == 5) { src = w.seg.p; bytes = (size_t)(w.T + 2) * 4; }
+    else if (which == 7) { src = w.counts.p; bytes = (size_t)w.T * 4; }
+    else if (which == 8) { src = w.es.p; bytes = Ep * 4; }
     else if (which == 6) { src = h->cmsg.p; bytes = (size_t)b.N_l * 12 * 4; }
     else return B200_ERR_INVALID;
   } else return B200_ERR_INVALID;

@@ -12,15 +12,12 @@
 #define SIG 32              // sigma / distance embedding width
 #define B200_MAX_CHUNKS 96
 
-struct DevPlan {            // device mirror of B200ConvPlan (pointers are device pointers)
+struct DevPlan {            // device mirror of B200ConvPlan (no pointers: the dense CG blocks live in c_cg_dense)
   int n_paths;
   B200Path paths[B200_MAX_PATHS];
   int in_dim, sh_dim, out_dim, z_numel, n_cols;
   int n_blocks;
   B200Block blocks[B200_MAX_BLOCKS];
-  int n_cg;
-  const int* cg_ijk;
-  const float* cg_val;
   int n_chunks;
   // chunk tables live in constant memory with the plan: they sit on the MMA issue path
   int chunk_col[B200_MAX_CHUNKS];

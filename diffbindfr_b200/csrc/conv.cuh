@@ -12,7 +12,11 @@
 #pragma once
 #include "common.cuh"
 
-__constant__ DevPlan c_plans[B200_N_PLANS];
+// Conv plans live in constant memory, one set per unit-width variant (192 / 144 / 96 weight columns per accumulator unit):
+// the content of a slot is a pure function of the static network spec, so handles with different conv kernels on one device
+// never overwrite each other's tables (each slot is written once per device, under a mutex, at b200dock_create).
+#define B200_PLAN_VARIANTS 3
+__constant__ DevPlan c_plans[B200_PLAN_VARIANTS * B200_N_PLANS];
 // dense Clebsch-Gordan blocks per (plan, path): C[i][j][k] with i<3 (in1), j<5 (sh), k<3 (out), zero padded
 __constant__ float c_cg_dense[B200_N_PLANS][B200_MAX_PATHS][45];
 
@@ -53,13 +57,16 @@ struct ConvArgs {
   const float* tabB;        // xin block 3 + x1 source, indexed by ed (mode 0) / bond atoms (mode 1)
   const int* bonds;         // mode 1 only
   int mode;                 // 0: conv layers, 1: pseudo-torque convs
-  int plan;
+  int plan;                 // index into c_plans (variant * B200_N_PLANS + plan id)
+  int cgp;                  // plan id for c_cg_dense
   const float* W1t; const float* b1;   // [144][144] ([in][out]), [144]
   const float* W2p;         // [n_cols][160]
-  float* H1;                // [E_pad][160]
-  float* H1_lo;             // optional: H1 - tf32(H1) for the 3xTF32 tensor-core mode (H1 then holds tf32(H1))
-  float* Zt;                // [tiles][z_numel][128]
-  float* msg;               // [E_pad][HS]
+  float* H1;                // [E_pad][160]  (exact SIMT mode only)
+  float* Zt;                // [tiles][z_numel][128]  (exact SIMT mode only)
+  float* msg;               // [E_pad][HS]  per-edge messages (kernels without the fused scatter epilogue)
+  const int* seg; const int* counts;   // first slot / edge count of every scatter target (k_scan_aligned)
+  float* agg;               // [T][HS]  sum of the messages of every target whose edges lie in ONE 32-slot chunk
+  float* part;              // [slots/32][2][HS]  partial sums of segments that cross a chunk boundary (tc_common.cuh)
   float inv_s1, inv_s2;     // fp16 mode: inverse power-of-two scales of the packed W1 / W2
 };
 struct ConvLaunch { ConvArgs c[4]; int n; int dbg; long long* trace; };   // dbg / trace: timing experiments only (B200DOCK_DBG, debug_set(1))
@@ -73,7 +80,7 @@ constexpr size_t PRO_SMEM = (size_t)(PRO_U_FLOATS + 144 * 144 + 9 * 128 + 2 * 12
 
 // Per 128-edge tile: (1) gather xin = [edge_emb | hA[:48] | hB[:48]] transposed into shared memory,
 // (2) H1 = relu(W1 xin + b1) with an 8x9 register tile per thread, staged through shared memory so the
-// 640-byte H1 rows leave coalesced (optionally split into TF32 hi/lo), (3) gather the x1 node rows
+// 640-byte H1 rows leave coalesced (), (3) gather the x1 node rows
 // coalesced into shared memory and contract them with the edge harmonics through the sparse CG tables.
 __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) {
   extern __shared__ float smem[];
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
       const int e0 = tile * TILE_E;
       __syncthreads();
       if (tid < TILE_E) {
-        Is[tid] = C.es[e0 + tid];
+        Is[tid] = max(C.es[e0 + tid], 0);            // es = -1: inert padding slot (its message is never reduced)
         Is[128 + tid] = C.ed[e0 + tid];
       }
       __syncthreads();
@@ -170,18 +177,7 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
           const float* src = Hst + e * PRO_HS_STRIDE + q * 4;
           float4 v = make_float4(src[0], src[1], src[2], src[3]);
           const size_t o = (size_t)(e0 + e) * KP + q * 4;
-          if (C.H1_lo) {
-            float4 hi, lo;
-            uint32_t hb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb); lo.x = v.x - hi.x;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb); lo.y = v.y - hi.y;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb); lo.z = v.z - hi.z;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb); lo.w = v.w - hi.w;
-            *reinterpret_cast<float4*>(C.H1 + o) = hi;
-            *reinterpret_cast<float4*>(C.H1_lo + o) = lo;
-          } else {
-            *reinterpret_cast<float4*>(C.H1 + o) = v;
-          }
+          *reinterpret_cast<float4*>(C.H1 + o) = v;
         }
       }
       __syncthreads();
@@ -205,7 +201,7 @@ __global__ void __launch_bounds__(PRO_THREADS, 1) k_conv_prologue(ConvLaunch L) 
           float shv[5];
 #pragma unroll
           for (int j = 0; j < 5; ++j) shv[j] = (j < d2) ? Ss[(pa.in2_off + j) * 128 + e] : 0.0f;
-          const float* cg = c_cg_dense[C.plan][p];
+          const float* cg = c_cg_dense[C.cgp][p];
           const float* xp = x1 + pa.in1_off;
           float* o = zt + (size_t)pa.z_off * TILE_E + e;
           if (d1 == 1 && k3 == 1) z_path<1, 1>(cg, shv, d2, xp, pa.U, half, 2, o);
@@ -321,64 +317,42 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_tp_simt(ConvLaunch L) {
 
 // ------------------------------------------------------------------------- node update
 struct LnParams { const float* shift; const float* weight; const float* bias; };
+struct AggSrc { const int* seg; const int* counts; const float* agg; const float* part; };
 struct NodeUpdateArgs {
   int N;
   float* h;                  // [N][HS] in place
-  const int* seg[2]; const float* msg[2]; LnParams ln[2];
+  AggSrc src[2]; LnParams ln[2];
   int plan;
 };
 
-// Segment sum of one source by WPN cooperating warps (warp w takes edges p0+w, p0+w+WPN, ...), 4 rows in
-// flight per lane; the partial sums meet in shared memory, then the node's first warp applies the mean and the
-// equivariant LayerNorm.  Result left in the first partial row (shared).
-template <int WPN>
-__device__ __forceinline__ void segment_partial(const DevPlan& P, const int* seg, const float* msg, int n, int w,
-                                                float* part /* [WPN][HS] */, int lane) {
-  const int p0 = seg[n], p1 = seg[n + 1];
-  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int e = p0 + w;
-  for (; e + 3 * WPN < p1; e += 4 * WPN) {
-    float v[4][6];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        int c = lane + 32 * q;
-        v[r][q] = (c < P.out_dim) ? msg[(size_t)(e + r * WPN) * HS + c] : 0.0f;
-      }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int q = 0; q < 6; ++q) s[q] += v[r][q];
-  }
-  for (; e < p1; e += WPN)
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      int c = lane + 32 * q;
-      if (c < P.out_dim) s[q] += msg[(size_t)e * HS + c];
-    }
+// row[c] = mean over the incoming edges of node n (scatter 'mean' with clamp(min=1) on the count, tpscore.py:190): the sums
+// come from the scatter epilogue (tc_common.cuh) - the node's own row when its segment sits inside one 32-slot chunk, otherwise
+// the partial rows of the chunks it crosses, added in chunk order.
+__device__ __forceinline__ void load_mean_row(const DevPlan& P, const AggSrc& S, int n, float* row, int lane) {
+  const int cnt = S.counts[n], sb = S.seg[n];
+  const int c0 = sb >> 5, c1 = (sb + cnt - 1) >> 5;
+  const float den = (float)max(cnt, 1);
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
-    int c = lane + 32 * q;
-    if (c < P.out_dim) part[w * HS + c] = s[q];
-  }
-}
-
-template <int WPN>
-__device__ __forceinline__ void mean_ln(const DevPlan& P, const int* seg, LnParams ln, int n, float* part, int lane) {
-  float* row = part;                                   // result overwrites the first partial row
-  const float cnt = (float)max(seg[n + 1] - seg[n], 1);
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    int c = lane + 32 * q;
+    const int c = lane + 32 * q;
     if (c < P.out_dim) {
-      float s = part[c];
-#pragma unroll
-      for (int w = 1; w < WPN; ++w) s += part[w * HS + c];
-      row[c] = s / cnt;
+      float v = 0.0f;
+      if (cnt > 0) {
+        if (c0 == c1) v = S.agg[(size_t)n * HS + c];
+        else {
+          v = S.part[((size_t)c0 * 2 + 1) * HS + c];
+          for (int cc = c0 + 1; cc < c1; ++cc) v += S.part[((size_t)cc * 2) * HS + c];
+          v += S.part[((size_t)c1 * 2) * HS + c];
+        }
+      }
+      row[c] = v / den;
     }
   }
   __syncwarp();
+}
+
+// equivariant LayerNorm (tpscore.py:20-107) of one message row held in shared memory, by one warp, in place
+__device__ __forceinline__ void ln_row(const DevPlan& P, LnParams ln, float* row, int lane) {
   float fm[B200_MAX_BLOCKS][3], scl[B200_MAX_BLOCKS];
   for (int b = 0; b < P.n_blocks; ++b) {
     const B200Block bl = P.blocks[b];
@@ -426,50 +400,32 @@ __device__ __forceinline__ void mean_ln(const DevPlan& P, const int* seg, LnPara
   __syncwarp();
 }
 
-// single-warp convenience wrapper (pseudo-torque read-outs)
-__device__ __forceinline__ void segment_mean_ln(const DevPlan& P, const int* seg, const float* msg, LnParams ln,
-                                                int n, float* row, int lane) {
-  segment_partial<1>(P, seg, msg, n, 0, row, lane);
-  __syncwarp();
-  mean_ln<1>(P, seg, ln, n, row, lane);
-}
-
-// h[n] += LN_0(mean_0) + LN_1(mean_1)  (tpscore.py:513-516); WPN warps cooperate on one node
-template <int WPN>
+// h[n] += LN_0(mean_0) + LN_1(mean_1)  (tpscore.py:513-516); one warp per node
 __global__ void __launch_bounds__(256) k_node_update(NodeUpdateArgs A) {
-  constexpr int NPB = 8 / WPN;                         // nodes per block
-  __shared__ float parts[8][HS];
+  __shared__ float rows[8][HS];
   const DevPlan& P = c_plans[A.plan];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int slot = wib / WPN, w = wib % WPN;
-  for (int base = blockIdx.x * NPB; base < A.N; base += gridDim.x * NPB) {
-    const int n = base + slot;
-    const bool valid = n < A.N;
+  for (int n = blockIdx.x * 8 + wib; n < A.N; n += gridDim.x * 8) {
     float acc[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       int c = lane + 32 * q;
-      acc[q] = (valid && w == 0 && c < P.out_dim) ? A.h[(size_t)n * HS + c] : 0.0f;
+      acc[q] = (c < P.out_dim) ? A.h[(size_t)n * HS + c] : 0.0f;
     }
     for (int s = 0; s < 2; ++s) {
-      if (valid) segment_partial<WPN>(P, A.seg[s], A.msg[s], n, w, parts[slot * WPN], lane);
-      if (WPN > 1) __syncthreads(); else __syncwarp();
-      if (valid && w == 0) {
-        mean_ln<WPN>(P, A.seg[s], A.ln[s], n, parts[slot * WPN], lane);
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          int c = lane + 32 * q;
-          if (c < P.out_dim) acc[q] += parts[slot * WPN][c];
-        }
-      }
-      if (WPN > 1) __syncthreads(); else __syncwarp();
-    }
-    if (valid && w == 0) {
+      load_mean_row(P, A.src[s], n, rows[wib], lane);
+      ln_row(P, A.ln[s], rows[wib], lane);
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
         int c = lane + 32 * q;
-        if (c < P.out_dim) A.h[(size_t)n * HS + c] = acc[q];
+        if (c < P.out_dim) acc[q] += rows[wib][c];
       }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      int c = lane + 32 * q;
+      if (c < P.out_dim) A.h[(size_t)n * HS + c] = acc[q];
     }
   }
 }

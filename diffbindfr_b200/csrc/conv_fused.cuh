@@ -1,459 +1,20 @@
-// MODE 4: fully fused tensor-product convolution (one kernel per layer, nothing per-edge in HBM but the message).
+// MODE 5: fused tensor-product convolution on tcgen05 (single CTA per 128-edge tile), one kernel per layer:
+// nothing per-edge goes to HBM but the message row (reduced afterwards by k_msg_scatter; the CTA-pair kernel of
+// conv_fused2.cuh fuses that reduction too).
 //
 // Per 128-edge tile (thread of the epilogue warps = TMEM lane = edge):
-//   1. gather xin = [edge_emb | hA[:48] | hB[:48] | 1] -> TF32 hi/lo -> tensor memory (A region)
-//   2. MMA1  D1[128,144] = xin . W1p^T   (3xTF32; first FC layer, bias through the ones column)
-//   3. H1 = relu(D1) -> TF32 hi/lo -> tensor memory (overwrites the A region; column 144 := 1)
-//   4. MMA2  D[128, N<=96] = H1 . W2p^T per chunk (3xTF32), W1/W2 streamed through one TMA ring
+//   1. gather xin = [edge_emb | hA[:48] | hB[:48] | 1], scale the row by a power of two, split into fp16 hi/lo -> tensor memory
+//   2. MMA1  D1[128,144] = xin . W1p^T   (first FC layer, bias through the ones column; 3 fp16 MMAs per K step)
+//   3. H1 = relu(D1) -> rescaled fp16 hi/lo -> tensor memory (overwrites the A region; column 144 := scale)
+//   4. MMA2  D[128,144] = H1 . W2p[unit]^T per 144-column unit, W1/W2 streamed through one TMA ring
 //   5. fold  msg[w,k] += D[u*Wd+w] * Z[u,k] with Z[u,k] = sum_i x1[u,i] M[i,k], M = CG . sh computed in registers;
 //      x1 (the gathered node row) sits in a per-thread shared-memory scratch row
 // Neither H1 nor the [E, weight_numel] weights nor Z are ever written to global memory
 // (the reference materialises [E, 7776] fp32 per conv).
 #pragma once
-#include <cuda_fp16.h>
-#include "conv_tc.cuh"
+#include "tc_common.cuh"
 
-#define F_NST 5
-#define F_BN 96
-#define F_D0 320
-#define F_X1S 169
-#define F16_BN 144                   // fp16 mode: unit width (columns) and ring depth
-#define F16_NST 3
-constexpr size_t F_SMEM = 1024 + (size_t)F_NST * 2 * F_BN * 128 + (size_t)128 * F_X1S * 4 + 256;
 constexpr size_t F16_SMEM = 1024 + (size_t)F16_NST * 2 * F16_BN * 128 + (size_t)128 * F_X1S * 4 + 256;
-
-struct FusedMaps { CUtensorMap w2[4], w2_lo[4], w1[4], w1_lo[4]; };
-
-// W1p[192][160]: row j = output channel (rows >= 144 zero), col k < 144 = W1[j][k], col 144 = b1[j]; TF32 hi / lo
-__global__ void k_build_w1p(const float* __restrict__ W1t, const float* __restrict__ b1, float* __restrict__ hi,
-                            float* __restrict__ lo) {
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 192 * KP; idx += gridDim.x * blockDim.x) {
-    int j = idx / KP, k = idx % KP;
-    float v = 0.0f;
-    if (j < 144) v = (k < 144) ? W1t[k * 144 + j] : (k == 144 ? b1[j] : 0.0f);
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    float h = __uint_as_float(hb);
-    hi[idx] = h; lo[idx] = v - h;
-  }
-}
-
-// fp32 W1p[192][160] (no split), source for the fp16 packing
-__global__ void k_build_w1p_f32(const float* __restrict__ W1t, const float* __restrict__ b1, float* __restrict__ out) {
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 192 * KP; idx += gridDim.x * blockDim.x) {
-    int j = idx / KP, k = idx % KP;
-    float v = 0.0f;
-    if (j < 144) v = (k < 144) ? W1t[k * 144 + j] : (k == 144 ? b1[j] : 0.0f);
-    out[idx] = v;
-  }
-}
-
-namespace tc {
-__device__ __forceinline__ void split_store32(uint32_t addr_hi, uint32_t addr_lo, float* v) {
-  float lo[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v[j]));
-    float hi = __uint_as_float(hb);
-    lo[j] = v[j] - hi; v[j] = hi;
-  }
-  tmem_st32(addr_hi, v);
-  tmem_st32(addr_lo, lo);
-}
-}  // namespace tc
-
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
-  constexpr int BN = F_BN, NST = F_NST;
-  constexpr uint32_t B_PART = BN * 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sB = base;                                              // [NST][2][96 x 128 B]
-  float* x1s = reinterpret_cast<float*>(sB + (size_t)NST * 2 * B_PART);   // [128][169] per-edge scratch rows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x1s + 128 * F_X1S);
-  uint64_t* x_full = bars;            uint64_t* h_full = bars + 1;  uint64_t* a_empty = bars + 2;
-  uint64_t* b_full = bars + 3;        uint64_t* b_empty = bars + 3 + NST;
-  uint64_t* d_full = bars + 3 + 2 * NST;  uint64_t* d_empty = d_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    tc::mbar_init(x_full, 128); tc::mbar_init(h_full, 128); tc::mbar_init(a_empty, 1);
-    for (int s = 0; s < NST; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc::fence_before();
-  __syncthreads();
-  tc::fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0)
-      for (int ci = 0; ci < L.n; ++ci) {
-        tc::prefetch_tmap(&maps.w2[ci]); tc::prefetch_tmap(&maps.w2_lo[ci]);
-        tc::prefetch_tmap(&maps.w1[ci]); tc::prefetch_tmap(&maps.w1_lo[ci]);
-      }
-    __syncwarp();
-    tc::Phase st;
-    int tiles_before = 0;
-    for (int ci = 0; ci < L.n; ++ci) {
-      const ConvArgs& C = L.c[ci];
-      const DevPlan& P = c_plans[C.plan];
-      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
-      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
-      tiles_before += ntile;
-      for (int tile = first; tile < ntile; tile += gridDim.x) {
-        for (int unit = -2; unit < P.n_chunks; ++unit) {
-          const CUtensorMap* mh = unit < 0 ? &maps.w1[ci] : &maps.w2[ci];
-          const CUtensorMap* ml = unit < 0 ? &maps.w1_lo[ci] : &maps.w2_lo[ci];
-          const int row0 = unit < 0 ? (unit + 2) * BN : P.chunk_col[unit];
-          for (int ka = 0; ka < TC_KATOMS; ++ka) {
-            tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
-            if (tc::elect_one()) {
-              tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
-              uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
-              tc::tma_load_2d(dst, mh, ka * 32, row0, &b_full[st.idx]);
-              tc::tma_load_2d(dst + B_PART, ml, ka * 32, row0, &b_full[st.idx]);
-            }
-            __syncwarp();
-            tc::advance(st, NST);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ======================================================================= MMA issuer
-    tc::Phase st, db;
-    uint32_t xpar = 0, hpar = 0;
-    int tiles_before = 0;
-    for (int ci = 0; ci < L.n; ++ci) {
-      const ConvArgs& C = L.c[ci];
-      const DevPlan& P = c_plans[C.plan];
-      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
-      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
-      tiles_before += ntile;
-      for (int tile = first; tile < ntile; tile += gridDim.x) {
-        tc::mbar_wait(x_full, xpar);
-        xpar ^= 1;
-        tc::fence_after();
-        for (int unit = -2; unit < P.n_chunks; ++unit) {
-          if (unit == 0) {                              // H1 must be in tensor memory before the W2 units
-            tc::mbar_wait(h_full, hpar);
-            hpar ^= 1;
-            tc::fence_after();
-          }
-          const int N = unit == -2 ? 96 : (unit == -1 ? 48 : P.chunk_n[unit]);
-          tc::mbar_wait(&d_empty[db.idx], db.par ^ 1);
-          tc::fence_after();
-          const uint32_t idesc = tc::make_idesc_tf32(128, N);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(F_D0 + db.idx * BN);
-          for (int ka = 0; ka < TC_KATOMS; ++ka) {
-            tc::mbar_wait(&b_full[st.idx], st.par);
-            tc::fence_after();
-            const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * 2 * B_PART);
-            const uint64_t dh = tc::make_desc(b_hi), dl = tc::make_desc(b_hi + B_PART);
-            if (tc::elect_one()) {
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) {
-                if (ka == TC_KATOMS - 1 && k8 == 3) continue;   // columns 152..159 are zero padding
-                const uint32_t a_hi = tmem_base + (uint32_t)(ka * 32 + k8 * 8), a_lo = a_hi + KP;
-                tc::mma_tf32_ts(d_tmem, a_lo, dh + (uint64_t)(k8 * 2), idesc, (ka | k8) ? 1u : 0u);
-                tc::mma_tf32_ts(d_tmem, a_hi, dl + (uint64_t)(k8 * 2), idesc, 1u);
-                tc::mma_tf32_ts(d_tmem, a_hi, dh + (uint64_t)(k8 * 2), idesc, 1u);
-              }
-              tc::mma_commit(&b_empty[st.idx]);
-              if (ka == TC_KATOMS - 1) {
-                tc::mma_commit(&d_full[db.idx]);
-                if (unit + 1 == P.n_chunks) tc::mma_commit(a_empty);
-              }
-            }
-            __syncwarp();
-            tc::advance(st, NST);
-          }
-          tc::advance(db, 2);
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ================================================== gather / H1 / epilogue warps (thread = edge)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* xrow = x1s + row * F_X1S;
-    tc::Phase db;
-    uint32_t apar = 0;
-    int tiles_before = 0;
-    for (int ci = 0; ci < L.n; ++ci) {
-      const ConvArgs& C = L.c[ci];
-      const DevPlan& P = c_plans[C.plan];
-      const int ntile = (*C.n_edges + TILE_E - 1) / TILE_E;
-      int first = (int)((blockIdx.x + gridDim.x - (tiles_before % gridDim.x)) % gridDim.x);
-      tiles_before += ntile;
-      for (int tile = first; tile < ntile; tile += gridDim.x) {
-        const int e = tile * TILE_E + row;
-        const int s = C.es[e], d = C.ed[e];
-        // ---- 1. xin -> tensor memory
-        tc::mbar_wait(a_empty, apar ^ 1);
-        apar ^= 1;
-        tc::fence_after();
-        {
-          const float4* pe = reinterpret_cast<const float4*>(C.emb + (size_t)e * NSC);
-          const float4* pa = reinterpret_cast<const float4*>(C.tabA + (size_t)(C.mode == 0 ? s : d) * HS);
-          const float4* pb0; const float4* pb1 = nullptr;
-          if (C.mode == 0) pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
-          else {
-            pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
-            pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
-          }
-#pragma unroll 1
-          for (int g = 0; g < 5; ++g) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int k4 = g * 8 + j;                 // float4 index along K (0..39)
-              float4 f;
-              if (k4 < 12) f = __ldg(pe + k4);
-              else if (k4 < 24) f = __ldg(pa + (k4 - 12));
-              else if (k4 < 36) {
-                f = __ldg(pb0 + (k4 - 24));
-                if (pb1) { float4 f2 = __ldg(pb1 + (k4 - 24)); f.x += f2.x; f.y += f2.y; f.z += f2.z; f.w += f2.w; }
-              } else f = make_float4(k4 == 36 ? 1.0f : 0.0f, 0.0f, 0.0f, 0.0f);
-              v[4 * j] = f.x; v[4 * j + 1] = f.y; v[4 * j + 2] = f.z; v[4 * j + 3] = f.w;
-            }
-            tc::split_store32(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(KP + g * 32), v);
-          }
-          tc::tmem_wait_st();
-          tc::fence_before();
-          tc::mbar_arrive(x_full);
-        }
-        // ---- x1 row -> per-thread scratch, edge harmonics -> registers
-        {
-          const float4* px = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
-          const int nq = (P.in_dim + 3) >> 2;
-          for (int qq = 0; qq < nq; ++qq) {
-            float4 f = __ldg(px + qq);
-            xrow[4 * qq] = f.x; xrow[4 * qq + 1] = f.y; xrow[4 * qq + 2] = f.z; xrow[4 * qq + 3] = f.w;
-          }
-        }
-        float shv[9];
-#pragma unroll
-        for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
-        // ---- 3. D1 -> relu -> H1 hi/lo -> tensor memory
-        {
-          tc::Phase p0 = db; tc::advance(db, 2);
-          tc::Phase p1 = db; tc::advance(db, 2);
-          tc::mbar_wait(&d_full[p0.idx], p0.par);
-          tc::mbar_wait(&d_full[p1.idx], p1.par);
-          tc::fence_after();
-          const uint32_t t0 = lane_base + (uint32_t)(F_D0 + p0.idx * BN), t1 = lane_base + (uint32_t)(F_D0 + p1.idx * BN);
-#pragma unroll 1
-          for (int g = 0; g < 5; ++g) {
-            float v[32];
-            if (g < 3) { tc::tmem_ld16(t0 + g * 32, v); tc::tmem_ld16(t0 + g * 32 + 16, v + 16); }
-            else if (g == 3) { tc::tmem_ld16(t1, v); tc::tmem_ld16(t1 + 16, v + 16); }
-            else {
-              tc::tmem_ld16(t1 + 32, v);
-#pragma unroll
-              for (int j = 16; j < 32; ++j) v[j] = 0.0f;
-            }
-            tc::tmem_wait_ld();
-            const int nrelu = (g < 4) ? 32 : 16;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < nrelu) v[j] = fmaxf(v[j], 0.0f);
-            if (g == 4) v[16] = 1.0f;                    // column 144: carries the second-layer bias
-            tc::split_store32(lane_base + (uint32_t)(g * 32), lane_base + (uint32_t)(KP + g * 32), v);
-          }
-          tc::tmem_wait_st();
-          tc::fence_before();
-          __syncwarp();
-          if (lane == 0) { tc::mbar_arrive(&d_empty[p0.idx]); tc::mbar_arrive(&d_empty[p1.idx]); }
-          tc::mbar_arrive(h_full);
-        }
-        // ---- 5. W2 units: fold with Z computed on the fly
-        float* mrow = C.msg + (size_t)e * HS;
-        float o[48];
-#pragma unroll
-        for (int i = 0; i < 48; ++i) o[i] = 0.0f;
-        int cur_path = -1;
-        float M[9];
-        for (int ch = 0; ch < P.n_chunks; ++ch) {
-          const int col0 = P.chunk_col[ch], N = P.chunk_n[ch];
-          const int pidx = P.chunk_path[ch];
-          const B200Path pa = P.paths[pidx];
-          const int d1 = 2 * pa.l1 + 1;
-          if (pidx != cur_path) {                        // M[i][k] = sum_j C[i][j][k] sh[j]
-            cur_path = pidx;
-            const float* cg = c_cg_dense[C.plan][pidx];
-            const int d2 = 2 * pa.l2 + 1;
-#pragma unroll
-            for (int ik = 0; ik < 9; ++ik) M[ik] = 0.0f;
-            for (int j = 0; j < d2; ++j) {
-              const float sj = shv[0] * (pa.in2_off + j == 0) + shv[1] * (pa.in2_off + j == 1) + shv[2] * (pa.in2_off + j == 2) +
-                               shv[3] * (pa.in2_off + j == 3) + shv[4] * (pa.in2_off + j == 4) + shv[5] * (pa.in2_off + j == 5) +
-                               shv[6] * (pa.in2_off + j == 6) + shv[7] * (pa.in2_off + j == 7) + shv[8] * (pa.in2_off + j == 8);
-#pragma unroll
-              for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) M[i * 3 + k] = fmaf(cg[(i * 5 + j) * 3 + k], sj, M[i * 3 + k]);
-            }
-          }
-          const int u0 = (col0 - pa.col_off) / pa.Wd, nu = N / pa.Wd;
-          const float* xp = xrow + pa.in1_off + u0 * d1;
-          tc::mbar_wait(&d_full[db.idx], db.par);
-          tc::fence_after();
-          const uint32_t taddr = lane_base + (uint32_t)(F_D0 + db.idx * BN);
-          if (pa.Wd == 48) {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[48];
-              tc::tmem_ld16(taddr + uu * 48, v); tc::tmem_ld16(taddr + uu * 48 + 16, v + 16); tc::tmem_ld16(taddr + uu * 48 + 32, v + 32);
-              float z = xp[uu * d1] * M[0];
-              if (d1 == 3) z = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], z));
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 48; ++w) o[w] = fmaf(v[w], z, o[w]);
-            }
-          } else {
-            for (int uu = 0; uu < nu; ++uu) {
-              float v[12];
-              tc::tmem_ld4(taddr + uu * 12, v); tc::tmem_ld4(taddr + uu * 12 + 4, v + 4); tc::tmem_ld4(taddr + uu * 12 + 8, v + 8);
-              const float x0 = xp[uu * d1];
-              float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
-              if (d1 == 3) {
-                const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
-                z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
-              }
-              tc::tmem_wait_ld();
-#pragma unroll
-              for (int w = 0; w < 12; ++w) {
-                o[w * 3] = fmaf(v[w], z0, o[w * 3]); o[w * 3 + 1] = fmaf(v[w], z1, o[w * 3 + 1]);
-                o[w * 3 + 2] = fmaf(v[w], z2, o[w * 3 + 2]);
-              }
-            }
-          }
-          tc::fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&d_empty[db.idx]);
-          tc::advance(db, 2);
-          bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
-          if (last) {
-            const int nout = (pa.Wd == 48) ? 48 : 36;
-#pragma unroll
-            for (int i = 0; i < 48; i += 4) {
-              if (i < nout) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-              o[i] = o[i + 1] = o[i + 2] = o[i + 3] = 0.0f;
-            }
-          }
-        }
-      }
-    }
-  }
-  tc::fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc::fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-
-namespace tc {
-__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // fp16 x fp16 -> fp32
-}
-__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-// power-of-two scale that maps a row maximum into [2^9, 2^10): keeps fp16 hi/lo splits normal
-__device__ __forceinline__ float row_scale(float mx) {
-  int ex = ((__float_as_int(mx) >> 23) & 0xff) - 127;
-  return __int_as_float((127 + 9 - ex) << 23);
-}
-// 64 fp32 values -> fp16 hi / lo pairs -> 32 + 32 tensor-memory columns (element 2c in the low half of column c)
-__device__ __forceinline__ void pack_store_f16(uint32_t addr_hi, uint32_t addr_lo, const float* v) {
-  float ph[32], pl[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {                       // packed conversions: one cvt.rn.f16x2.f32 per pair and per term
-    const __half2 h = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v[2 * c] - hf.x, v[2 * c + 1] - hf.y);
-    ph[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
-    pl[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
-  }
-  tmem_st32(addr_hi, ph);
-  tmem_st32(addr_lo, pl);
-}
-}  // namespace tc
-
-namespace tc {
-// Software-pipelined fold of one 144-column unit (thread = edge = TMEM lane): the tensor-memory load of the next 16 (12)
-// accumulator columns is in flight while the FMAs of the current ones run, instead of a load -> wait -> FMA round trip per
-// input channel.  o[] are the thread's message accumulators; xp the gathered node row (shared memory), M = CG . sh.
-__device__ __forceinline__ void fold_unit_w48(uint32_t taddr, const float* xp, int d1, const float* M, float zs, float* o) {
-  float va[16], vb[16];
-  tmem_ld16(taddr, va);
-  float z[3];
-#pragma unroll
-  for (int uu = 0; uu < 3; ++uu) {
-    float t = xp[uu * d1] * M[0];
-    if (d1 == 3) t = fmaf(xp[uu * 3 + 1], M[3], fmaf(xp[uu * 3 + 2], M[6], t));
-    z[uu] = t * zs;
-  }
-#pragma unroll
-  for (int c = 0; c < 9; ++c) {                       // 9 chunks of 16 columns: u = c / 3, w offset (c % 3) * 16
-    float* cur = (c & 1) ? vb : va;
-    float* nxt = (c & 1) ? va : vb;
-    tmem_wait_ld();
-    if (c + 1 < 9) tmem_ld16(taddr + (c + 1) * 16, nxt);
-    const float2 zz = make_float2(z[c / 3], z[c / 3]);
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {                 // packed fp32 FMAs (FFMA2, sm_100): two accumulators per instruction, IEEE per lane
-      const int w = (c % 3) * 16 + j;
-      const float2 r = __ffma2_rn(make_float2(cur[j], cur[j + 1]), zz, make_float2(o[w], o[w + 1]));
-      o[w] = r.x; o[w + 1] = r.y;
-    }
-  }
-}
-// Wd = 12, three output components per channel: accumulators are kept COMPONENT-MAJOR, o[k * 12 + w] (the caller un-permutes when
-// it stores the block), so that channel pairs (w, w+1) of one component are adjacent registers for the packed FMAs.
-__device__ __forceinline__ void fold_unit_w12(uint32_t taddr, const float* xp, int d1, const float* M, float zs, float* o) {
-  float va[12], vb[12];
-  tmem_ld4(taddr, va); tmem_ld4(taddr + 4, va + 4); tmem_ld4(taddr + 8, va + 8);
-#pragma unroll
-  for (int uu = 0; uu < 12; ++uu) {
-    float* cur = (uu & 1) ? vb : va;
-    float* nxt = (uu & 1) ? va : vb;
-    const float x0 = xp[uu * d1];
-    float z0 = x0 * M[0], z1 = x0 * M[1], z2 = x0 * M[2];
-    if (d1 == 3) {
-      const float xa = xp[uu * 3 + 1], xb = xp[uu * 3 + 2];
-      z0 = fmaf(xa, M[3], fmaf(xb, M[6], z0)); z1 = fmaf(xa, M[4], fmaf(xb, M[7], z1)); z2 = fmaf(xa, M[5], fmaf(xb, M[8], z2));
-    }
-    const float2 zz[3] = {make_float2(z0 * zs, z0 * zs), make_float2(z1 * zs, z1 * zs), make_float2(z2 * zs, z2 * zs)};
-    tmem_wait_ld();
-    if (uu + 1 < 12) {
-      const uint32_t a = taddr + (uu + 1) * 12;
-      tmem_ld4(a, nxt); tmem_ld4(a + 4, nxt + 4); tmem_ld4(a + 8, nxt + 8);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int w = 0; w < 12; w += 2) {
-        const float2 r = __ffma2_rn(make_float2(cur[w], cur[w + 1]), zz[k], make_float2(o[k * 12 + w], o[k * 12 + w + 1]));
-        o[k * 12 + w] = r.x; o[k * 12 + w + 1] = r.y;
-      }
-  }
-}
-}  // namespace tc
 
 // MODE 5: the fused kernel with FP16 hi/lo splits (3 x kind::f16 MMAs per K-step, K = 192 halves): same
 // error-compensation scheme, twice the tensor throughput and ~60 % of the W streaming of the TF32 variant.
@@ -516,13 +77,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           for (int ka = 0; ka < KATOMS; ++ka) {
             tc::mbar_wait(&b_empty[st.idx], st.par ^ 1);
             if (tc::elect_one()) {
-              if (L.dbg & 32) tc::mbar_arrive(&b_full[st.idx]);   // timing experiment: no weight streaming
-              else {
               tc::mbar_expect_tx(&b_full[st.idx], 2 * B_PART);
               uint8_t* dst = sB + (size_t)st.idx * 2 * B_PART;
               tc::tma_load_2d(dst, mh, ka * 64, row0, &b_full[st.idx]);
               tc::tma_load_2d(dst + B_PART, ml, ka * 64, row0, &b_full[st.idx]);
-              }
             }
             __syncwarp();
             tc::advance(st, NST);
@@ -579,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
 #pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
             TRW(3 + ka, tc::mbar_wait(&b_full[ka], bpar));
-            if (!(L.dbg & 8)) tc::fence_after();
+            tc::fence_after();
             if (tc::elect_one()) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
@@ -638,7 +196,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
       tiles_before += ntile;
       for (int tile = first; tile < ntile; tile += gridDim.x) {
         const int e = tile * TILE_E + row;
-        const int s = C.es[e], d = C.ed[e];
+        const int s = max(C.es[e], 0), d = C.ed[e];     // es = -1: inert padding slot, its message row is never reduced
         float sx = 1.0f, shh = 1.0f;
         // ---- 1. xin -> tensor memory
         TRE_BEGIN();
@@ -655,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
             pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
             pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
           }
-          if (!(L.dbg & 1)) {
+          {
           float4 xf[36];                                 // the whole edge-input row in flight at once
 #pragma unroll
           for (int k4 = 0; k4 < 12; ++k4) xf[k4] = __ldg(pe + k4);
@@ -707,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
               o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
             }
         };
-        if (!(L.dbg & 4)) x1_batch(0);
+        x1_batch(0);
         float shv[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
@@ -722,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
           float mx = 1.0f;
 #pragma unroll 1
-          for (int g = (L.dbg & 2) ? 9 : 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
+          for (int g = 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
             float v[16];
             tc::tmem_ld16(t0 + g * 16, v);
             tc::tmem_wait_ld();
@@ -732,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           shh = tc::row_scale(mx);
           const float sc1 = inv1 * shh;
 #pragma unroll 1
-          for (int g = (L.dbg & 2) ? 3 : 0; g < 3; ++g) {                  // pass 2: relu, scale, fp16 hi/lo, store
+          for (int g = 0; g < 3; ++g) {                  // pass 2: relu, scale, fp16 hi/lo, store
             float v[64];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -754,10 +312,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           tc::mbar_arrive(h_full);
           TRE_END(4);
         }
-        if (!(L.dbg & 4)) {
 #pragma unroll 1
-          for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
-        }
+        for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
         // ---- 5. W2 units: fold with Z computed on the fly
         float* mrow = C.msg + (size_t)e * HS;
         float o[48];
@@ -772,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           const int d1 = 2 * pa.l1 + 1;
           if (pidx != cur_path) {                        // M[i][k] = sum_j C[i][j][k] sh[j]
             cur_path = pidx;
-            const float* cg = c_cg_dense[C.plan][pidx];
+            const float* cg = c_cg_dense[C.cgp][pidx];
             const int d2 = 2 * pa.l2 + 1;
 #pragma unroll
             for (int ik = 0; ik < 9; ++ik) M[ik] = 0.0f;
@@ -795,8 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (L.dbg & 16) {                            // timing experiment: no fold
-          } else if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);   // every unit is 144 columns wide (packer.py asserts it)
+          if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);   // every unit is 144 columns wide (packer.py asserts it)
           else tc::fold_unit_w12(taddr, xp, d1, M, zs, o);                     // accumulators component-major, see the store below
           tc::fence_before();
           __syncwarp();
@@ -837,45 +392,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
 #undef TRE_END
 }
 
-struct FusedExtra { const float* W1hi[4]; const float* W1lo[4]; const float* W2lo[4]; uint64_t w2_rows[4]; };
-
 static inline int conv_fused_init() {
-  if (cudaFuncSetAttribute(k_conv_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) != cudaSuccess) return 1;
   return cudaFuncSetAttribute(k_conv_fused16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F16_SMEM) == cudaSuccess ? 0 : 1;
 }
-
-#define KH 192   // fp16 K (halves), padded to 3 swizzle atoms
-
-// fp32 [rows][160] (K-major, packed W2p / W1p) -> fp16 hi / lo [rows_out][192] scaled by `scale`
-__global__ void k_build_w16(const float* __restrict__ src, int rows, int rows_out, float scale, __half* __restrict__ hi,
-                            __half* __restrict__ lo) {
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)rows_out * KH; idx += (size_t)gridDim.x * blockDim.x) {
-    int j = (int)(idx / KH), k = (int)(idx % KH);
-    float v = (j < rows && k < KP) ? src[(size_t)j * KP + k] * scale : 0.0f;
-    __half h = __float2half_rn(v);
-    hi[idx] = h; lo[idx] = __float2half_rn(v - __half2float(h));
-  }
-}
-
-__global__ void k_absmax(const float* __restrict__ src, size_t n, float* __restrict__ out) {
-  float m = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // non-negative floats order as ints
-}
-
-static inline int tc_make_map16(CUtensorMap* m, const void* ptr, uint64_t rows, uint32_t box_rows) {
-  cuuint64_t gdim[2] = {KH, rows};
-  cuuint64_t gstr[1] = {KH * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 1;
-}
-
-struct Fused16Extra { const void* W1hi[4]; const void* W1lo[4]; const void* W2hi[4]; const void* W2lo[4]; uint64_t w2_rows[4]; };
 
 static inline int launch_conv_fused16(const ConvLaunch& L, const Fused16Extra& X, int grid, cudaStream_t st) {
   if (!g_encode) return 1;
@@ -888,19 +407,5 @@ static inline int launch_conv_fused16(const ConvLaunch& L, const Fused16Extra& X
     if (tc_make_map16(&maps.w1_lo[i], X.W1lo[i], 192, F16_BN)) return 5;
   }
   k_conv_fused16<<<grid, TC_THREADS, F16_SMEM, st>>>(L, maps);
-  return cudaGetLastError() == cudaSuccess ? 0 : 6;
-}
-
-static inline int launch_conv_fused(const ConvLaunch& L, const FusedExtra& X, int grid, cudaStream_t st) {
-  if (!g_encode) return 1;
-  FusedMaps maps;
-  memset(&maps, 0, sizeof maps);
-  for (int i = 0; i < L.n; ++i) {
-    if (tc_make_map(&maps.w2[i], L.c[i].W2p, X.w2_rows[i], F_BN)) return 2;
-    if (tc_make_map(&maps.w2_lo[i], X.W2lo[i], X.w2_rows[i], F_BN)) return 3;
-    if (tc_make_map(&maps.w1[i], X.W1hi[i], 192, F_BN)) return 4;
-    if (tc_make_map(&maps.w1_lo[i], X.W1lo[i], 192, F_BN)) return 5;
-  }
-  k_conv_fused<<<grid, TC_THREADS, F_SMEM, st>>>(L, maps);
   return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }

@@ -12,12 +12,11 @@
 //                                                                        b_full[6] (1 + TMA bytes of both CTAs)
 //   per CTA, arrived on by the leader's tcgen05.commit.multicast:        b_empty[6], d_full[2], a_empty
 #pragma once
-#include <cooperative_groups.h>
-#include "conv_fused.cuh"
+#include "tc_common.cuh"
 
 #define F2_NST 6
 #define F2_HB 72                      // B rows (weight columns) per CTA per unit
-constexpr size_t F2_SMEM = 1024 + (size_t)F2_NST * 2 * F2_HB * 128 + (size_t)128 * F_X1S * 4 + 512;
+constexpr size_t F2_SMEM = 1024 + (size_t)F2_NST * 2 * F2_HB * 128 + (size_t)128 * F_X1S * 4 + 512 + (size_t)4 * 32 * SCAT_STRIDE * 4;
 
 namespace tc {
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -86,6 +85,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
   uint64_t* b_full = bars + 3;        uint64_t* b_empty = bars + 3 + NST;
   uint64_t* d_full = bars + 3 + 2 * NST;  uint64_t* d_empty = d_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
+  float* scat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [4 warps][32][SCAT_STRIDE] scatter scratch
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
@@ -233,6 +233,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     float* xrow = x1s + row * F_X1S;
+    float* scr = scat + q * 32 * SCAT_STRIDE;
     const uint32_t x_full0 = tc::map_to_cta(x_full, 0), h_full0 = tc::map_to_cta(h_full, 0);
     const uint32_t d_empty0[2] = {tc::map_to_cta(&d_empty[0], 0), tc::map_to_cta(&d_empty[1], 0)};
     tc::Phase db;
@@ -264,7 +265,10 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
         const bool live = tile < ntile;                 // odd tile count: the peer recomputes the last tile, stores nothing
         if (!live) tile = ntile - 1;
         const int e = tile * TILE_E + row;
-        const int s = C.es[e], d = C.ed[e];
+        const int s_raw = C.es[e], d = C.ed[e];
+        const int s = max(s_raw, 0);                    // es = -1: inert padding slot
+        // run structure of this warp's 32 slots for the scatter epilogue (duplicate tile of an odd pair: nothing to reduce)
+        const ScatterCtx SC = scatter_ctx(C.seg, C.counts, e, live ? s_raw : -1, lane);
         float sx = 1.0f, shh = 1.0f;
         // ---- 1. xin -> tensor memory
         TRE_BEGIN();
@@ -381,7 +385,6 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
 #pragma unroll 1
         for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
         // ---- 5. W2 units: fold with Z computed on the fly
-        float* mrow = C.msg + (size_t)e * HS;
         float o[48];
 #pragma unroll
         for (int i = 0; i < 48; ++i) o[i] = 0.0f;
@@ -394,7 +397,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           const int d1 = 2 * pa.l1 + 1;
           if (pidx != cur_path) {                        // M[i][k] = sum_j C[i][j][k] sh[j]
             cur_path = pidx;
-            const float* cg = c_cg_dense[C.plan][pidx];
+            const float* cg = c_cg_dense[C.cgp][pidx];
             const int d2 = 2 * pa.l2 + 1;
 #pragma unroll
             for (int ik = 0; ik < 9; ++ik) M[ik] = 0.0f;
@@ -424,17 +427,16 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           if (lane == 0) tc::mbar_arrive_cluster(d_empty0[db.idx]);
           tc::advance(db, 2);
           bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
-          if (last) {
-            const int nout = (pa.Wd == 48) ? 48 : 36;
+          if (last) {                                    // message block complete: segmented sum over the warp's 32 edges
+            float* my = scr + lane * SCAT_STRIDE;
+            if (pa.Wd == 48) {
 #pragma unroll
-            for (int i = 0; i < 48; i += 4) {
-              if (i < nout && live) {
-                if (pa.Wd == 48) *reinterpret_cast<float4*>(mrow + pa.out_off + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-                else *reinterpret_cast<float4*>(mrow + pa.out_off + i) =         // message element i = (channel i / 3, component i % 3)
-                    make_float4(o[(i % 3) * 12 + i / 3], o[((i + 1) % 3) * 12 + (i + 1) / 3], o[((i + 2) % 3) * 12 + (i + 2) / 3],
-                                o[((i + 3) % 3) * 12 + (i + 3) / 3]);
-              }
+              for (int i = 0; i < 48; ++i) my[i] = o[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 36; ++i) my[i] = o[(i % 3) * 12 + i / 3];   // message element i = (channel i / 3, component i % 3)
             }
+            scatter_block(scr, pa.Wd == 48 ? 48 : 36, pa.out_off, SC, C.agg, C.part, lane);
 #pragma unroll
             for (int i = 0; i < 48; ++i) o[i] = 0.0f;
           }

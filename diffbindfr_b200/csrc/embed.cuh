@@ -134,9 +134,17 @@ __global__ void __launch_bounds__(128) k_edge_feat(EdgeFeatArgs A) {
   __syncthreads();
   (void)in_dim;
   const float coeff = A.mlp.coeff()[0];
-  const int E = *A.n_edges;
+  const int E = (*A.n_edges + TILE_E - 1) / TILE_E * TILE_E;   // whole tiles: the conv kernels read every slot of a tile
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
     int s = A.es[e], d = A.ed[e];
+    if (s < 0) {                                    // inert padding slot (graph.cuh): defined, finite operands for the conv
+      float4* o4 = reinterpret_cast<float4*>(A.emb + (size_t)e * NSC);
+#pragma unroll
+      for (int j = 0; j < NSC / 4; ++j) o4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ns = (KIND == G_TOR || KIND == G_SC) ? 8 : 9;
+      for (int j = 0; j < ns; ++j) A.sh[(size_t)e * ns + j] = 0.0f;
+      continue;
+    }
     float vx, vy, vz;
     int g = 0;
     float bsh[5];

@@ -22,6 +22,7 @@ struct GraphArgs {
   // torsion bonds
   const int* tor_bonds; int n_tor;
   const int* sc_bonds; int n_sc;
+  const int* tor_ptr; const int* sc_ptr; int B;   // per-graph ranges of the torsion / chi bond lists
   // cap helpers
   const int* lig_jmax; const int* atom_jmax;
 };
@@ -134,40 +135,102 @@ __global__ void __launch_bounds__(256) k_graph_count(GraphArgs A, int T, int* __
   }
 }
 
-// Exclusive scan of counts[T] into seg_ptr[T+1] by one block (T is at most a few hundred thousand).
-__global__ void k_scan(const int* __restrict__ counts, int T, int* __restrict__ seg_ptr) {
-  __shared__ int part[1024];
-  int tid = threadIdx.x, nt = blockDim.x;
-  int chunk = (T + nt - 1) / nt;
-  int lo = min(tid * chunk, T), hi = min(lo + chunk, T);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += counts[i];
-  part[tid] = s;
+// Graph id of scatter target t and the per-graph target ranges of a family.
+template <int KIND>
+__device__ __forceinline__ int target_graph(const GraphArgs& A, int t) {
+  if (KIND == G_LIG || KIND == G_AL) return A.lig_batch[t];
+  if (KIND == G_ATOM || KIND == G_LA) return A.atom_batch[t];
+  if (KIND == G_TOR) return A.lig_batch[A.tor_bonds[2 * t]];
+  return A.atom_batch[A.sc_bonds[2 * t]];
+}
+template <int KIND>
+__device__ __forceinline__ const int* target_ptr(const GraphArgs& A) {
+  if (KIND == G_LIG || KIND == G_AL) return A.lig_ptr;
+  if (KIND == G_ATOM || KIND == G_LA) return A.atom_ptr;
+  if (KIND == G_TOR) return A.tor_ptr;
+  return A.sc_ptr;
+}
+
+// Block-wide exclusive scan of one value per thread (Hillis-Steele over 1024 partials); returns the exclusive prefix,
+// *total = sum over the block.
+__device__ __forceinline__ int block_excl_scan(int v, int* part, int* total) {
+  const int tid = threadIdx.x, nt = blockDim.x;
   __syncthreads();
-  for (int o = 1; o < nt; o <<= 1) {   // Hillis-Steele inclusive scan
-    int v = (tid >= o) ? part[tid - o] : 0;
+  part[tid] = v;
+  __syncthreads();
+  for (int o = 1; o < nt; o <<= 1) {
+    int x = (tid >= o) ? part[tid - o] : 0;
     __syncthreads();
-    part[tid] += v;
+    part[tid] += x;
     __syncthreads();
   }
-  int run = part[tid] - s;
+  *total = part[nt - 1];
+  return part[tid] - v;
+}
+
+// counts[T] -> seg_ptr[T+2] by one block: seg_ptr[t] = first edge slot of target t, with every GRAPH's edge range starting
+// at a multiple of 32 slots (the gaps are padded with inert edges by k_graph_fill).  Tiles of the conv kernels are 128
+// consecutive slots = four warps of 32; because a graph always starts on a warp boundary, the partition of its edges into
+// 32-slot chunks - and with it the summation order of the fused scatter - does not depend on which other graphs share the
+// batch (batch-composition independence, tests/test_gpu_parity.py).  seg_ptr[T] = number of slots (multiple of 32),
+// seg_ptr[T+1] = number of real edges.  If the slots exceed the workspace capacity the family is made EMPTY on the device
+// (all counts and seg_ptr zeroed) and err_flag is raised, so every later kernel is a no-op until the host reports it.
+template <int KIND>
+__global__ void __launch_bounds__(1024) k_scan_aligned(GraphArgs A, int T, int cap, int* __restrict__ counts,
+                                                       int* __restrict__ seg_ptr, int* __restrict__ gpad,
+                                                       int* __restrict__ err_flag) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int chunk = (T + nt - 1) / nt;
+  const int lo = min(tid * chunk, T), hi = min(lo + chunk, T);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += counts[i];
+  int total;
+  int run = block_excl_scan(s, part, &total);
   for (int i = lo; i < hi; ++i) { seg_ptr[i] = run; run += counts[i]; }
-  if (tid == nt - 1) seg_ptr[T] = part[tid];
+  __syncthreads();
+  // graph level: padded size of every graph's range, exclusive scan -> shift of the graph's targets
+  const int* gp = target_ptr<KIND>(A);
+  const int gchunk = (A.B + nt - 1) / nt;
+  const int glo = min(tid * gchunk, A.B), ghi = min(glo + gchunk, A.B);
+  int gs = 0;
+  for (int g = glo; g < ghi; ++g) {
+    const int t0 = gp[g], t1 = gp[g + 1];
+    const int r0 = t0 < T ? seg_ptr[t0] : total, r1 = t1 < T ? seg_ptr[t1] : total;
+    gs += (r1 - r0 + 31) & ~31;
+  }
+  int slots;
+  int grun = block_excl_scan(gs, part, &slots);
+  for (int g = glo; g < ghi; ++g) {
+    const int t0 = gp[g], t1 = gp[g + 1];
+    const int r0 = t0 < T ? seg_ptr[t0] : total, r1 = t1 < T ? seg_ptr[t1] : total;
+    gpad[g] = grun - r0;
+    grun += (r1 - r0 + 31) & ~31;
+  }
+  __syncthreads();
+  const bool over = slots > cap;
+  for (int i = lo; i < hi; ++i) {
+    if (over) { seg_ptr[i] = 0; counts[i] = 0; }
+    else seg_ptr[i] += gpad[target_graph<KIND>(A, i)];
+  }
+  if (tid == 0) {
+    seg_ptr[T] = over ? 0 : slots;
+    seg_ptr[T + 1] = over ? 0 : total;
+    if (over) atomicMax(err_flag, 1 + KIND);
+  }
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) k_graph_fill(GraphArgs A, int T, const int* __restrict__ seg_ptr, int cap,
-                                                    int* __restrict__ es, int* __restrict__ ed, int* __restrict__ eaux,
-                                                    int* __restrict__ err_flag) {
-  int total = seg_ptr[T];
-  if (total > cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(err_flag, 1 + KIND);
-    return;
-  }
+__global__ void __launch_bounds__(256) k_graph_fill(GraphArgs A, int T, const int* __restrict__ seg_ptr,
+                                                    const int* __restrict__ counts, int cap,
+                                                    int* __restrict__ es, int* __restrict__ ed, int* __restrict__ eaux) {
+  const int slots = seg_ptr[T];
+  if (slots == 0) return;                      // empty family (or overflow: k_scan_aligned emptied it and raised the flag)
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < T; t += warps) {
     int p = seg_ptr[t];
+    const int end = p + counts[t];
     if (KIND == G_LIG) {
       const int b0 = A.bond_ptr[t], nb = A.bond_ptr[t + 1] - b0;
       for (int b = lane; b < nb; b += 32) { es[p + b] = t; ed[p + b] = A.bond_dst[b0 + b]; eaux[p + b] = A.bond_eid[b0 + b]; }
@@ -190,11 +253,12 @@ __global__ void __launch_bounds__(256) k_graph_fill(GraphArgs A, int T, const in
       }
       p += n;
     }
-  }
-  // pad the tail of the last 128-edge tile with a harmless self edge
-  int padded = min(((total + TILE_E - 1) / TILE_E) * TILE_E, cap);
-  for (int p = total + blockIdx.x * blockDim.x + threadIdx.x; p < padded; p += gridDim.x * blockDim.x) {
-    es[p] = 0; ed[p] = 0;
-    if (eaux) eaux[p] = -1;
+    // inert slots between this target's last edge and the next target's first one (non-empty only at the end of a graph:
+    // alignment to 32) and, after the last target, up to the end of the last 128-slot tile: es = -1 marks "no edge"
+    const int nxt = (t + 1 < T) ? seg_ptr[t + 1] : min(((slots + TILE_E - 1) / TILE_E) * TILE_E, cap);
+    for (int q = end + lane; q < nxt; q += 32) {
+      es[q] = -1; ed[q] = 0;
+      if (eaux) eaux[q] = -1;
+    }
   }
 }

@@ -21,12 +21,13 @@ struct CenterArgs {
   const float* fc;                           // W1t[96][96] b1[96] W2t[96][336] b2[336]
   const float* h_lig;
   float* cmsg;                               // [N_l][12]
+  int plan;                                  // c_plans index of the centre conv
 };
 
 // One block (128 threads) per ligand atom = per centre edge.
 __global__ void __launch_bounds__(128) k_center_edge(CenterArgs A) {
   __shared__ float rbf[SIG], hid[NSC], xin[96], h1[96], w[336], z[512], sh[9], x1[HS];
-  const DevPlan& P = c_plans[B200_PLAN_FINAL];
+  const DevPlan& P = c_plans[A.plan];
   const int a = blockIdx.x, tid = threadIdx.x;
   const int g = A.lig_batch[a];
   const float vx = A.lig_pos[3 * a] - A.centre[3 * g], vy = A.lig_pos[3 * a + 1] - A.centre[3 * g + 1],
@@ -72,12 +73,13 @@ __global__ void __launch_bounds__(128) k_center_edge(CenterArgs A) {
     for (int idx = tid; idx < pa.U * k3; idx += 128) {
       int u = idx / k3, k = idx % k3;
       float acc = 0.0f;
-      for (int c = pa.cg_off; c < pa.cg_off + pa.cg_n; ++c) {
-        int ijk = P.cg_ijk[c];
-        if (((ijk >> 16) & 255) != k) continue;
-        int i = ijk & 255, j = (ijk >> 8) & 255;
-        acc += P.cg_val[c] * x1[pa.in1_off + u * d1 + i] * sh[pa.in2_off + j];
-      }
+      const float* cg = c_cg_dense[B200_PLAN_FINAL][p];      // dense C[i][j][k]; same (i, j) order as the sparse table
+      const int d2 = 2 * pa.l2 + 1;
+      for (int i = 0; i < d1; ++i)
+        for (int j = 0; j < d2; ++j) {
+          const float cv = cg[(i * 5 + j) * 3 + k];
+          if (cv != 0.0f) acc += cv * x1[pa.in1_off + u * d1 + i] * sh[pa.in2_off + j];
+        }
       z[pa.z_off + idx] = acc;
     }
   }
@@ -156,7 +158,7 @@ __global__ void k_center_head(CenterHeadArgs A) {
 }
 
 struct TorHeadArgs {
-  int n; const int* seg; const float* msg; LnParams ln;
+  int n; int plan; AggSrc src; LnParams ln;
   const float* mlp;            // W0t[96][48] w3[48]
   const float* norm2;          // [n]
   float* out;
@@ -164,10 +166,11 @@ struct TorHeadArgs {
 
 __global__ void __launch_bounds__(256) k_tor_head(TorHeadArgs A) {
   __shared__ float rows[8][HS];
-  const DevPlan& P = c_plans[B200_PLAN_TOR];
+  const DevPlan& P = c_plans[A.plan];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   for (int b = blockIdx.x * 8 + wib; b < A.n; b += gridDim.x * 8) {
-    segment_mean_ln(P, A.seg, A.msg, A.ln, b, rows[wib], lane);
+    load_mean_row(P, A.src, b, rows[wib], lane);
+    ln_row(P, A.ln, rows[wib], lane);
     float part = 0.0f;
     for (int j = lane; j < NSC; j += 32) {
       float acc = 0.0f;

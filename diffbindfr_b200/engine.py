@@ -22,6 +22,7 @@ _lib = None
 
 EXPORTS = ["b200dock_create", "b200dock_destroy", "b200dock_last_error", "b200dock_version",
            "b200dock_load_weights", "b200dock_score", "b200dock_sample", "b200dock_sample_host",
+           "b200dock_set_deferred_check", "b200dock_check",
            "b200dock_last_edge_counts", "b200dock_last_launch_count", "b200dock_set_profiling",
            "b200dock_tp_kernel_time_ms", "b200dock_debug_tap", "b200dock_debug_set",
            "b200dock_mdn_load_weights", "b200dock_mdn_score",
@@ -58,6 +59,8 @@ def load_library(path: Optional[str] = None):
     lib.b200dock_sample.argtypes = [C.c_void_p, C.POINTER(batch_mod.CBatch), C.POINTER(CStep), C.c_int] + [C.c_void_p] * 6
     lib.b200dock_sample_host.argtypes = [C.c_void_p, C.POINTER(batch_mod.CBatch), C.POINTER(CStep), C.c_int] + [C.c_void_p] * 4 + [
         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
+    lib.b200dock_set_deferred_check.argtypes = [C.c_void_p, C.c_int]
+    lib.b200dock_check.argtypes = [C.c_void_p, C.c_void_p]
     lib.b200dock_last_edge_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.b200dock_last_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.b200dock_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -103,12 +106,9 @@ def sinusoidal_embedding(t: torch.Tensor, dim: int = 32, scale: float = 1000.0) 
 
 
 class Engine:
-    """One handle = one device.  ``conv_kernel``: 0 SIMT fp32 (exact), 1 tcgen05 3xTF32 (H1 in smem),
-    2 tcgen05 single TF32 (fast, ~1e-3), 3 tcgen05 3xTF32 with H1 resident in tensor memory,
-    4 fully fused tcgen05 3xTF32 conv (both FC layers + fold in one kernel),
-    5 the fused kernel with FP16 hi/lo error-compensated MMAs and per-row scaling (fp32-grade),
-    6 mode 5 on CTA pairs (tcgen05 cta_group::2: the weight operand is split across two SMs; bit-identical to 5; default),
-    7 / 8 fp16 main product + two e4m3 cross-term MMAs (single CTA / CTA pairs; opt-in, ~5e-5), 9 mode 5 with two fold warpgroups."""
+    """One handle = one device.  ``conv_kernel``: 0 exact fp32 SIMT contraction (cross-check), 5 fused tcgen05 kernel with FP16
+    hi/lo error-compensated MMAs and per-row scaling (fp32-grade; per-edge message rows + a separate segmented scatter),
+    6 the same on CTA pairs (tcgen05 cta_group::2) with the scatter fused into the epilogue (default; bit-identical to 5)."""
 
     def __init__(self, device: int = 0, conv_kernel: int = 6):
         if not torch.cuda.is_available():

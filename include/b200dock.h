@@ -4,9 +4,20 @@
  * Plain C: raw device/host pointers, sizes, a cudaStream_t passed as void*, int status codes.
  * No torch types, no exceptions across the boundary.  One handle per (process, device); a handle
  * is not thread-safe (the reference drives one nn.Module from one Python thread,
- * druglib/datasets/builder.py:177-183).  All calls are asynchronous on the caller's stream
- * except where stated; the caller owns every input/output buffer, the library owns only the
- * workspace inside the handle (grown lazily, freed by b200dock_destroy).
+ * druglib/datasets/builder.py:177-183).  The caller owns every input/output buffer, the library owns only
+ * the workspace inside the handle (grown lazily, freed by b200dock_destroy).
+ *
+ * Synchronisation, per entry point:
+ *   b200dock_create / destroy / load_weights / mdn_load_* : synchronous (device-wide copies).
+ *   b200dock_score / b200dock_sample : all kernels are enqueued on the caller's stream (plus one internal side stream
+ *       joined back before return); the call then ENDS WITH ONE cudaStreamSynchronize that reads back the capacity flag
+ *       and the edge counts (B200_ERR_CAPACITY is reported here).  b200dock_set_deferred_check(h, 1) removes that
+ *       synchronisation: the calls return with the work merely enqueued and b200dock_check(h, stream) delivers the
+ *       verdict whenever the caller chooses to synchronise.  A family whose edge list overflows is emptied ON THE DEVICE
+ *       (no out-of-bounds access); the results of that evaluation are then meaningless and the status says so.
+ *   b200dock_sample_host : synchronous (H2D, sampling, D2H, one stream synchronisation).
+ *   b200dock_mdn_encode / mdn_score : asynchronous on the caller's stream, no synchronisation.
+ *   b200dock_debug_tap, b200dock_tp_kernel_time_ms : synchronous (tests / benchmarks only).
  *
  * Reference interfaces replaced (paths under /root/reference):
  *   b200dock_score   <- TensorProductModel.forward(data) -> (tr, rot, tor, sc_tor)
@@ -87,12 +98,9 @@ typedef struct {
 
 typedef struct {
   B200ConvPlan plans[B200_N_PLANS];
-  int32_t conv_kernel;      /* 0 SIMT fp32, 1 tcgen05 3xTF32 (A in smem), 2 tcgen05 TF32, 3 tcgen05 3xTF32 (A in TMEM),
-                               4 fully fused tcgen05 3xTF32 conv,
-                               5 fused conv with FP16 hi/lo MMAs + per-row scaling (fp32-grade),
-                               6 mode 5 on CTA pairs (cta_group::2; bit-identical to 5; default),
-                               7 / 8 fp16 main product + two e4m3 cross-term MMAs (single CTA / CTA pairs; opt-in, ~5e-5 on scores),
-                               9 mode 5 with two gather/fold warpgroups (experiment) */
+  int32_t conv_kernel;      /* 0 exact fp32 SIMT (cross-check), 5 fused tcgen05 conv with FP16 hi/lo MMAs + per-row scaling
+                               (fp32-grade; message rows + separate scatter), 6 the same on CTA pairs (cta_group::2) with the
+                               scatter fused into the epilogue (default; bit-identical to 5) */
   int32_t reserved[7];
   const int32_t* atom14_group;  /* [21][14] restype_atom14_to_rigid_group (protein_constants.py:1177-1199) */
   /* sparse CG tables of the pseudo-torque product harmonics: triples (2,2,0), (1,2,1), (2,2,1) */
@@ -161,6 +169,7 @@ typedef struct {
   float* torsion_angle;           /* [N_r][5]  in/out */
   const int32_t* sc_bonds;        /* [n_sc][2] torsion_edge_index[sc_torsion_edge_mask] (atom ids j, k) */
   const int32_t* sc_index;        /* [N_r][4] rank of (r, chi) among masked entries, or -1 */
+  const int32_t* sc_ptr;          /* [B+1] chi bonds per graph (sc_bonds is grouped by graph) */
 } B200Batch;
 
 /* Per-evaluation conditioning written by set_time (scFlex.py:104-122); per graph so that
@@ -204,6 +213,10 @@ int b200dock_score(B200Handle* h, const B200Batch* batch, const B200Cond* cond,
 int b200dock_sample(B200Handle* h, B200Batch* batch, const B200Step* steps, int n_steps,
                     const float* time_emb /* host [n_steps][32] */, const float* noise,
                     float* lig_traj, float* atom14_out, float* atom14_traj, void* stream);
+
+/* Deferred end-of-call check (see "Synchronisation" above). */
+int b200dock_set_deferred_check(B200Handle* h, int on);
+int b200dock_check(B200Handle* h, void* stream);
 
 /* Same with HOST pointers everywhere (batch arrays, noise, outputs): stages through pinned memory,
  * copies H2D, samples, copies the results D2H and synchronises the stream before returning.
@@ -284,8 +297,9 @@ int b200dock_tp_kernel_time_ms(B200Handle* h, double* ms, int64_t* launches);
 #define B200_TAP_EDGES 2      /* int32 pairs (s, d) of conv `arg` (0 lig, 1 atom, 2 al, 3 la, 4 tor, 5 sc) */
 #define B200_TAP_H_LIG0 3     /* embeddings before layer 0 */
 #define B200_TAP_H_ATOM0 4
-#define B200_TAP_CONV_BUF 5   /* arg = conv*16 + which; which: 0 emb[E][48], 1 sh[E][9|8], 2 H1[E][160],
-                                 3 Zt[tiles][z][128], 4 msg[E][168], 5 seg_ptr[T+1] (int32), 6 centre msg [N_l][12] */
+#define B200_TAP_CONV_BUF 5   /* arg = conv*16 + which; which: 0 emb[E][48], 1 sh[E][9|8], 2 H1[E][160] (kernel 0),
+                                 3 Zt[tiles][z][128] (kernel 0), 4 msg[E][168] (kernels 0, 5), 5 seg_ptr[T+2] (int32: first slot of
+                                 every target, [T] = slots, [T+1] = real edges), 6 centre msg [N_l][12], 7 counts[T], 8 es[slots] */
 /* Debug knobs (tests / tools only): key 0 = number of interaction layers to run (default 6); key 1 = wait-cycle accounting of the
  * fused conv kernels on (1) / off (0): 148 CTAs x 32 int64 counters (slots 0..7 MMA-issuing warp, 8..15 one fold warp; only filled by a
  * library built with -DB200DOCK_TRACE), read back with b200dock_debug_tap(what = 7). */

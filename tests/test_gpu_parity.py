@@ -13,9 +13,9 @@ from helpers import conditioning, load_golden, rmsd
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,4,5,6,7,8,9").split(",") if k]
+KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,5,6").split(",") if k]
 # fp32 score tolerance: |cuda - oracle_fp32| <= RTOL * max|oracle| (fp32 oracle itself is ~2e-6 from fp64)
-RTOL = {0: 2e-4, 1: 2e-4, 2: 5e-2, 3: 2e-4, 4: 2e-4, 5: 2e-4, 6: 2e-4, 7: 2e-4, 8: 2e-4, 9: 2e-4}
+RTOL = {0: 2e-4, 5: 2e-4, 6: 2e-4, 10: 2e-4}
 
 
 @pytest.fixture(scope="module")
@@ -188,7 +188,7 @@ def test_plugin_forward_and_sample_mirror_reference_interface(sd):
     assert rmsd(lig, gs["lig_traj"][-1]) <= 1e-3 and rmsd(a14, gs["atom14_final"]) <= 1e-3
 
 
-@pytest.mark.parametrize("kernel,tol", [(5, 2e-4), (8, 4e-4)])
+@pytest.mark.parametrize("kernel,tol", [(5, 2e-4), (6, 2e-4)])
 @pytest.mark.parametrize("w1_scale,w2_scale", [(40.0, 1e-3), (0.02, 30.0)])
 def test_fp16_mode_is_robust_to_weight_and_activation_scale(sd, w1_scale, w2_scale, kernel, tol):
     """Modes 5-8 split operands into fp16 hi/lo with exact power-of-two scaling (per conv for W, per edge row
@@ -301,7 +301,7 @@ def test_sharded_sampling_with_sliced_noise_equals_full_batch(sd):
 def test_cfgA_shape_trajectory_against_oracle(sd):
     """Trajectory parity at the BASELINE pose shape (36 residues / ~300 pocket atoms / 30 ligand atoms; 2 poses x 10 steps keeps the
     CPU oracle at ~20 s): the default kernel stays within 1e-3 A RMSD of the fp32 oracle at every step (measured ~1e-5, the
-    fp32-vs-fp64 distance of the oracle itself is 2e-5 after 20 steps); the opt-in e4m3 kernel is looser and bounded at 5e-3 A."""
+    fp32-vs-fp64 distance of the oracle itself is 2e-5 after 20 steps)."""
     from diffbindfr_b200.engine import Engine
     kw = dict(synth.WORKLOADS["cfgA"]); kw["n_poses"] = 2
     b = synth.make_batch(**kw, seed=0)
@@ -316,10 +316,140 @@ def test_cfgA_shape_trajectory_against_oracle(sd):
     osampler.sample(sd, b, noise=noise, cfg=cfg, trace=trace,
                     rot_norm_fn=lambda x: min(sch, key=lambda s: abs(s.rot_sigma - x)).rot_score_norm,
                     tor_norm_fn=lambda x: min(sch, key=lambda s: abs(s.sc_tor_sigma - x)).tor_score_norm2)
-    for kernel, tol in ((6, 1e-3), (8, 5e-3)):
+    for kernel, tol in ((6, 1e-3),):
         eng = make_engine(kernel, sd)
         lig, a14, lig_traj, _ = eng.sample(b, sch, Engine.pack_noise(noise), trajectory=True)
         torch.cuda.synchronize()
         worst = max(rmsd(lig_traj[s].cpu(), trace[s]["lig_pos"]) for s in range(n))
         print(f"kernel {kernel}: worst-step ligand RMSD vs fp32 oracle {worst:.2e} A, atom14 {rmsd(a14.cpu(), trace[-1]['atom14']):.2e} A")
         assert worst <= tol and rmsd(a14.cpu(), trace[-1]["atom14"]) <= tol, (kernel, worst)
+
+
+def _sorted_rows(pairs, feats):
+    """Rows [s, d, feat...] in a canonical order (ligand graphs hold duplicate (s, d) pairs: bond + radius edge)."""
+    rows = torch.cat([torch.as_tensor(pairs, dtype=torch.float64), feats.double()], 1)
+    order = np.lexsort(rows.numpy().T[::-1])
+    return rows[order]
+
+
+@pytest.mark.parametrize("kernel", [5, 6])
+def test_embedding_layers_match_oracle_taps(sd, kernel):
+    """Layer-level parity: node embeddings (SimpleLinear / AtomEncoder), edge embeddings (GaussianSmearing +
+    SimpleLinear) and spherical harmonics of every conv graph against the oracle's intermediate tensors; then the node features
+    after ONE interaction layer (fused conv + scatter + LayerNorm + residual)."""
+    eng = make_engine(kernel, sd)
+    b = synth.make_batch(n_complex=2, n_poses=1, n_res=18, n_lig=(12, 20), seed=5)
+    c = conditioning(b, tr_sigma=2.0, t=0.55)
+    taps = {}
+    d = dict(b); d.update(c)
+    omodel.score_model(sd, d, torch.float32, taps=taps)
+    eng.debug_set(0, 0)                               # no interaction layer: h_lig / h_atom are the embeddings
+    run_score(eng, b, c)
+    h_lig0 = torch.from_numpy(eng.tap(0)).reshape(-1, 168)[:, :48]
+    h_atom0 = torch.from_numpy(eng.tap(1)).reshape(-1, 168)[:, :48]
+    assert (h_lig0 - taps["h_lig0"]).abs().max() <= 1e-5 * max(1.0, taps["h_lig0"].abs().max().item())
+    assert (h_atom0 - taps["h_atom0"]).abs().max() <= 1e-5 * max(1.0, taps["h_atom0"].abs().max().item())
+    refs = [(taps["lig_ei"], taps["lig_ea"], taps["lig_sh"]), (taps["atom_ei"], taps["atom_ea"], taps["atom_sh"]),
+            (taps["la_ei"], taps["la_ea"], taps["la_sh"])]
+    for ci, (ei, ea, sh) in enumerate(refs):
+        pairs = eng.tap(2, ci, dtype=np.int32).reshape(-1, 2)
+        es = eng.tap(5, ci * 16 + 8, dtype=np.int32)
+        real = torch.from_numpy(es >= 0)
+        emb = torch.from_numpy(eng.tap(5, ci * 16 + 0)).reshape(-1, 48)[:real.numel()][real]
+        shd = torch.from_numpy(eng.tap(5, ci * 16 + 1)).reshape(-1, 9)[:real.numel()][real]
+        mine = _sorted_rows(pairs, torch.cat([emb, shd], 1))
+        ref = _sorted_rows(ei.T.numpy(), torch.cat([ea, sh], 1))
+        assert mine.shape == ref.shape, ci
+        assert torch.equal(mine[:, :2], ref[:, :2]), ci
+        assert (mine[:, 2:] - ref[:, 2:]).abs().max() <= 2e-5 * max(1.0, ref[:, 2:].abs().max().item()), ci
+    eng.debug_set(0, 1)                               # one interaction layer
+    run_score(eng, b, c)
+    h_lig1 = torch.from_numpy(eng.tap(0)).reshape(-1, 168)[:, :taps["h_lig1"].shape[1]]
+    h_atom1 = torch.from_numpy(eng.tap(1)).reshape(-1, 168)[:, :taps["h_atom1"].shape[1]]
+    assert (h_lig1 - taps["h_lig1"]).abs().max() <= 1e-4 * max(1.0, taps["h_lig1"].abs().max().item())
+    assert (h_atom1 - taps["h_atom1"]).abs().max() <= 1e-4 * max(1.0, taps["h_atom1"].abs().max().item())
+    eng.debug_set(0, 6)
+
+
+def test_edge_slots_are_graph_aligned(engines):
+    """Layout contract of the fused scatter: every graph's edge range starts on a 32-slot boundary, padding slots carry es = -1,
+    the slots of a target are contiguous and the real-edge count excludes the padding."""
+    eng = engines[sorted(engines)[0]]
+    b = synth.make_batch(n_complex=3, n_poses=2, n_res=(9, 20), n_lig=(8, 19), seed=12)
+    run_score(eng, b, conditioning(b))
+    lb = torch.as_tensor(b["lig_node_batch"]).numpy(); ab = torch.as_tensor(b["rec_atm_pos_batch"]).numpy()
+    for ci, tb in ((0, lb), (1, ab), (2, lb), (3, ab)):
+        seg = eng.tap(5, ci * 16 + 5, dtype=np.int32)
+        cnt = eng.tap(5, ci * 16 + 7, dtype=np.int32)
+        es = eng.tap(5, ci * 16 + 8, dtype=np.int32)
+        T = len(cnt)
+        slots, real = int(seg[T]), int(seg[T + 1])
+        assert slots % 32 == 0 and real == int(cnt.sum()) == int((es[:slots] >= 0).sum())
+        assert (es[slots:] == -1).all()
+        first = np.flatnonzero(np.r_[True, tb[1:] != tb[:-1]])
+        assert (seg[first] % 32 == 0).all(), ci
+        for t in range(T):
+            assert (es[seg[t]:seg[t] + cnt[t]] == t).all()
+
+
+def test_capacity_overflow_is_reported_cleanly(sd):
+    """an atom set denser than the workspace bound (64 neighbours per atom on average) must give B200_ERR_CAPACITY,
+    not out-of-bounds accesses: the overflowing family is emptied on the device; the handle stays usable afterwards."""
+    eng = make_engine(6, sd)
+    good = synth.make_batch(n_complex=1, n_poses=2, n_res=16, n_lig=14, seed=2)
+    c = conditioning(good)
+    want = run_score(eng, good, c)
+    bad = dict(good)
+    g = torch.Generator().manual_seed(0)
+    bad["rec_atm_pos"] = torch.rand(good["rec_atm_pos"].shape, generator=g) * 0.5       # every atom within 4 A of every other
+    with pytest.raises(RuntimeError, match="overflowed"):
+        eng.score(bad, c["t"], c["tr_sigma"], c["rot_score_norm"], c["tor_score_norm2"], c["sc_tor_score_norm2"])
+    torch.cuda.synchronize()
+    again = run_score(eng, good, c)
+    for a, w in zip(again, want):
+        assert torch.equal(a, w)
+
+
+def test_ode_branch_matches_oracle(sd):
+    """scFlex.py:162-165,199-200: type='ode' perturbs by 0.5 g^2 score dt without noise."""
+    from diffbindfr_b200.engine import Engine
+    b = synth.make_batch(**synth.WORKLOADS["tiny"], seed=8)
+    n = 4
+    sch, noise = _steps_and_noise(b, n, 3)
+    cfg = dict(osampler.CFG); cfg["actual_steps"] = n; cfg["type"] = "ode"
+    trace = []
+    osampler.sample(sd, b, noise=noise[:n], cfg=cfg, trace=trace,
+                    rot_norm_fn=lambda x: min(sch, key=lambda s: abs(s.rot_sigma - x)).rot_score_norm,
+                    tor_norm_fn=lambda x: min(sch, key=lambda s: abs(s.sc_tor_sigma - x)).tor_score_norm2)
+    eng = make_engine(6, sd)
+    lig, a14, lig_traj, _ = eng.sample(b, sch, Engine.pack_noise(noise[:n]), trajectory=True, ode=True)
+    torch.cuda.synchronize()
+    for s in range(n):
+        assert rmsd(lig_traj[s].cpu(), trace[s]["lig_pos"]) <= 1e-4, s
+    assert rmsd(a14.cpu(), trace[-1]["atom14"]) <= 1e-4
+    lig_sde, _, _, _ = eng.sample(b, sch, Engine.pack_noise(noise[:n]))
+    torch.cuda.synchronize()
+    assert rmsd(lig_sde.cpu(), lig.cpu()) > 1e-2       # the SDE run with the same scores + noise ends somewhere else
+
+
+def test_bench_batch_trajectory_against_oracle_fixture(sd):
+    """The EXACT batch bench.py times (cfg-A seed 0, noise seed 1, 40 poses x 20 steps) against the committed CPU-oracle
+    trajectory (tools/make_golden_bench.py, 12 min of CPU): north_star bar 1e-3 A RMSD on the final ligand coordinates, checked at
+    every step and for the side chains."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden_bench import bench_noise
+    from helpers import batch_checksum
+    g = load_golden("bench_cfgA_s20.pt")
+    b = synth.make_batch(**synth.WORKLOADS[g["workload"]], seed=g["seed"])
+    assert batch_checksum(b) == g["batch_checksum"]
+    sch = schedule.make_schedule()[:g["steps"]]
+    z = bench_noise(b, g["steps"], g["noise_seed"])
+    for kernel in (6,):
+        eng = make_engine(kernel, sd)
+        lig, a14, lig_traj, _ = eng.sample(b, sch, z, trajectory=True)
+        torch.cuda.synchronize()
+        per_step = [rmsd(lig_traj[s].cpu(), g["lig_traj"][s]) for s in range(g["steps"])]
+        print(f"kernel {kernel}: 40x20 bench batch vs oracle: final ligand RMSD {per_step[-1]:.2e} A, worst step {max(per_step):.2e} A, "
+              f"atom14 {rmsd(a14.cpu(), g['atom14_final']):.2e} A")
+        assert max(per_step) <= 1e-3 and rmsd(a14.cpu(), g["atom14_final"]) <= 1e-3

@@ -275,15 +275,15 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    kname = {0: "k_conv_tp_simt (fp32 SIMT)", 1: "k_conv_tp_tc<1> (tcgen05 3xTF32, H1 in smem)", 2: "k_conv_tp_tc<2> (tcgen05 TF32)", 3: "k_conv_tp_tc3 (tcgen05 3xTF32, H1 in TMEM)", 4: "k_conv_fused (tcgen05 3xTF32, both FC layers + fold fused)", 5: "k_conv_fused16 (tcgen05 3xFP16 split, fused)", 6: "k_conv_fused16x2 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, fused)", 7: "k_conv_fused8 (tcgen05 fp16 main + 2 e4m3 cross-term MMAs, fused)", 8: "k_conv_fused8x2 (tcgen05 cta_group::2 CTA pairs, fp16 main + 2 e4m3 cross-term MMAs, fused)", 9: "k_conv_fused16wg (tcgen05 3xFP16 split, fused, two gather/fold warpgroups)"}[args.conv_kernel]
+    kname = {0: "k_conv_tp_simt (fp32 SIMT)", 1: "k_conv_tp_tc<1> (tcgen05 3xTF32, H1 in smem)", 2: "k_conv_tp_tc<2> (tcgen05 TF32)", 3: "k_conv_tp_tc3 (tcgen05 3xTF32, H1 in TMEM)", 4: "k_conv_fused (tcgen05 3xTF32, both FC layers + fold fused)", 5: "k_conv_fused16 (tcgen05 3xFP16 split, fused)", 6: "k_conv_fused16x2 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, fused)", 7: "k_conv_fused8 (tcgen05 fp16 main + 2 e4m3 cross-term MMAs, fused)", 8: "k_conv_fused8x2 (tcgen05 cta_group::2 CTA pairs, fp16 main + 2 e4m3 cross-term MMAs, fused)", 9: "k_conv_fused16wg (tcgen05 3xFP16 split, fused, two gather/fold warpgroups)", 10: "k_conv_v3 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, two A buffers in TMEM, fused scatter)"}[args.conv_kernel]
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
             "kernel": kname, "kernel_ms_per_step": tp_ms / K, "kernel_share_of_step": tp_ms / ms_total,
             "launches_per_step": tp_launches / K, "algorithmic_flops_per_step": f_tp, "peak_source": peak_src,
             "algorithmic_flops_per_launch": f_tp * K / max(tp_launches, 1),
-            "mma_slots_per_algorithmic_mac": {5: 2.9, 6: 2.9, 9: 2.9, 7: 2.0, 8: 2.0}.get(args.conv_kernel, 1.0),
-            "issued_mma_tflops": (achieved * {5: 2.9, 6: 2.9, 9: 2.9, 7: 2.0, 8: 2.0}.get(args.conv_kernel, 1.0)) if achieved else None,
-            "issued_frac_of_peak": (achieved * {5: 2.9, 6: 2.9, 9: 2.9, 7: 2.0, 8: 2.0}.get(args.conv_kernel, 1.0) / peak_tf) if achieved else None,
+            "mma_slots_per_algorithmic_mac": {5: 2.9, 6: 2.9, 10: 2.9}.get(args.conv_kernel, 1.0),
+            "issued_mma_tflops": (achieved * {5: 2.9, 6: 2.9, 10: 2.9}.get(args.conv_kernel, 1.0)) if achieved else None,
+            "issued_frac_of_peak": (achieved * {5: 2.9, 6: 2.9, 10: 2.9}.get(args.conv_kernel, 1.0) / peak_tf) if achieved else None,
             "note": "achieved = algorithmic FLOPs of all tensor-product launches of the timed region / their summed CUDA-event time; "
                     "the default kernel issues 29 fp16 MMAs per 10 K-steps (hi/lo error compensation; issued_* fields count them; e4m3 slots of modes 7/8 counted at the fp16 slot cost); "
                     "traffic = mean DRAM bytes per launch over one step (8 launches) from the committed ncu capture"}
@@ -354,7 +354,7 @@ def main():
         cpu = cpu_baseline(n_poses=args.cpu_baseline_poses, steps=1)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 4: "tf32x3", 5: "fp16x3", 6: "fp16x3", 7: "fp16+2xe4m3", 8: "fp16+2xe4m3", 9: "fp16x3"}[args.conv_kernel], "data": "synthetic",
+            "dtype": {0: "f32", 1: "tf32x3", 2: "tf32", 3: "tf32x3", 4: "tf32x3", 5: "fp16x3", 6: "fp16x3", 10: "fp16x3"}[args.conv_kernel], "data": "synthetic",
             "config": {"workload": f"{args.workload}: 1 complex x 40 poses x 36 residues (~300 pocket atoms) x 30 ligand atoms per GPU"
                        if args.workload == "cfgA" else f"{args.workload}: {workload_kwargs(args.workload)} per GPU",
                        "poses_per_gpu": int(b["num_graphs"]), "pocket_atoms": int(b["rec_atm_pos"].shape[0]),

@@ -15,6 +15,7 @@
 #include "tc_common.cuh"
 #include "conv_fused.cuh"
 #include "conv_fused2.cuh"
+#include "conv_v3.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
 #include "mdn.cuh"
@@ -48,9 +49,10 @@ struct ConvW {                  // views into the device weight blob
   const __half *W1h16 = nullptr, *W1l16 = nullptr, *W2h16 = nullptr, *W2l16 = nullptr; float inv_s1 = 1.f, inv_s2 = 1.f;
 };
 
-// conv kernels: 0 exact fp32 SIMT (192-column units), 5 fused tcgen05 single CTA, 6 fused tcgen05 CTA pairs + fused scatter (144)
-inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6; }
-inline int variant_of_kernel(int k) { return k == 0 ? 0 : 1; }
+// conv kernels: 0 exact fp32 SIMT (192-column units), 5 fused tcgen05 single CTA, 6 fused tcgen05 CTA pairs + fused scatter (144),
+// 10 the pair kernel re-pipelined over two A buffers with 96-column units (no tile-transition bubble)
+inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6 || k == 10; }
+inline int variant_of_kernel(int k) { return k == 0 ? 0 : (k == 10 ? 2 : 1); }
 inline bool kernel_keeps_msg(int k) { return k == 0 || k == 5; }
 
 }  // namespace
@@ -210,7 +212,8 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const Fused16Extra& F, cudaStr
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
   const int k = h->cfg.conv_kernel;
-  if (k == 6) rc = launch_conv_fused16x2(L, F, h->tp_grid, st);
+  if (k == 10) rc = launch_conv_v3(L, F, h->tp_grid, st);
+  else if (k == 6) rc = launch_conv_fused16x2(L, F, h->tp_grid, st);
   else if (k == 5) rc = launch_conv_fused16(L, F, h->tp_grid, st);
   else {
     k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
@@ -510,7 +513,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   *out = h;
   h->device = device;
   h->cfg = *cfg;
-  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs)");
+  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs, 10 re-pipelined pair kernel)");
   h->variant = variant_of_kernel(cfg->conv_kernel);
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -557,7 +560,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
   CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
   CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
-  if (tc_init() || conv_fused_init() || conv_fused2_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  if (tc_init() || conv_fused_init() || conv_fused2_init() || conv_v3_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
   h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
   return B200_OK;
 }

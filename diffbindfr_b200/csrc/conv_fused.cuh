@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
         {
           const float4* pe = reinterpret_cast<const float4*>(C.emb + (size_t)e * NSC);
           const float4* pa = reinterpret_cast<const float4*>(C.tabA + (size_t)(C.mode == 0 ? s : d) * HS);
-          const float4* pb0; const float4* pb1 = nullptr;
-          if (C.mode == 0) pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
+          const float4* pb0; const float4* pb1;        // pb1 always points at a valid row: the compiler may speculate the __ldg loads
+          if (C.mode == 0) pb0 = pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)d * HS);
           else {
             pb0 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s] * HS);
             pb1 = reinterpret_cast<const float4*>(C.tabB + (size_t)C.bonds[2 * s + 1] * HS);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_fused16(ConvLaunch L, co
           for (int k4 = 0; k4 < 12; ++k4) xf[12 + k4] = __ldg(pa + k4);
 #pragma unroll
           for (int k4 = 0; k4 < 12; ++k4) xf[24 + k4] = __ldg(pb0 + k4);
-          if (pb1) {
+          if (C.mode != 0) {
 #pragma unroll
             for (int k4 = 0; k4 < 12; ++k4) {
               float4 f2 = __ldg(pb1 + k4);

@@ -31,6 +31,7 @@ from . import spec
 from .engine import Engine
 
 _TP_BUFFER = re.compile(r"(\.tp\.|^final_tp_tor\.|\.final_tp_tor\.)")
+_TP_LOCAL = re.compile(r"^(tp|final_tp_tor)\.")
 
 
 def _get(obj, key, default=None):
@@ -54,7 +55,24 @@ def _pop(obj, key):
     return v
 
 
-class _Node(nn.Module):
+class _DropE3nnBuffers:
+    """e3nn ``TensorProduct`` modules register non-parameter buffers (``tp.weight`` (empty), ``tp.output_mask``, compiled-graph
+    constants) whose exact keys cannot be enumerated without e3nn.  They carry no learned state, so every module of the plugin
+    drops the keys ``<prefix>tp.*`` / ``<prefix>final_tp_tor.*`` from the incoming state dict BEFORE torch's bookkeeping sees
+    them.  This hook is what both loaders call per module: ``nn.Module.load_state_dict`` and the reference's own
+    ``druglib/core/runner/checkpoint.py:32-100`` (which recurses with ``module._load_from_state_dict(..., strict=True, ...)``
+    from the top-level ``DiffBindFR`` and is what ``DiffBindFR/app/predict.py:118-125`` uses with ``strict=True``)."""
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        n = len(prefix)
+        for k in [k for k in state_dict if k.startswith(prefix) and _TP_LOCAL.match(k[n:])]:
+            del state_dict[k]
+        if hasattr(self, "_packed"):
+            self._packed = False            # device copy of the weights is stale from here on
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+
+
+class _Node(_DropE3nnBuffers, nn.Module):
     """Container used to reproduce the reference's dotted parameter names exactly."""
 
 
@@ -78,7 +96,7 @@ _EXPECTED_CFG = dict(ns=spec.NS, nv=spec.NV, sh_lmax=2, lig_cutoff=5, atom_cutof
                      time_emb_type="sinusoidal")
 
 
-class TensorProductModel(nn.Module):
+class TensorProductModel(_DropE3nnBuffers, nn.Module):
     """B200 implementation of the SE(3)-equivariant score network (same state_dict as the reference)."""
 
     def __init__(self, cfg=None, conv_kernel: int = 6, device: Optional[int] = None):
@@ -105,11 +123,10 @@ class TensorProductModel(nn.Module):
         self._engine: Optional[Engine] = None
         self._packed = False
 
-    # e3nn registers non-parameter buffers under *.tp.* whose keys cannot be enumerated without e3nn;
-    # accept and ignore them so that reference checkpoints load with strict=True.
+    # the e3nn buffer keys (*.tp.*, final_tp_tor.*) are dropped per module by _DropE3nnBuffers._load_from_state_dict, so
+    # reference checkpoints load with strict=True through torch's loader and through the reference's own
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        sd = {k: v for k, v in state_dict.items() if not _TP_BUFFER.search(k)}
-        out = super().load_state_dict(sd, strict=strict, **kw)
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._packed = False
         return out
 
@@ -310,8 +327,32 @@ class KarmaDock(nn.Module):
         return self.scoring(lig_s, x["lig_pos"], pro_s, x, 5.0, int(x["lig_batch"][-1]) + 1)
 
 
+def rebind_scorer() -> bool:
+    """``common.engines.Scorer`` instantiates the name ``KarmaDock`` of its own module namespace
+    (DiffBindFR/common/engines.py:29-31,246): rebinding that name routes the MDN rescoring stage of ``predict.py`` through the
+    device scorer without any source edit.  No-op (False) when the reference package cannot be imported."""
+    import sys
+    done = False
+    try:
+        import importlib
+        mods = [sys.modules.get("DiffBindFR.common.engines") or importlib.import_module("DiffBindFR.common.engines")]
+    except Exception:
+        mods = []
+    for m in mods:
+        if m is not None and hasattr(m, "KarmaDock"):
+            m.KarmaDock = KarmaDock
+            done = True
+    sc = sys.modules.get("DiffBindFR.scoring")
+    if sc is not None and hasattr(sc, "KarmaDock"):
+        sc.KarmaDock = KarmaDock
+        done = True
+    return done
+
+
 def register(force: bool = True) -> bool:
-    """Register the plugin classes in the reference's registries when ``druglib`` is importable."""
+    """Register the plugin classes in the reference's registries when ``druglib`` is importable, and rebind the MDN scorer
+    class ``common.engines.Scorer`` builds (``rebind_scorer``)."""
+    rebind_scorer()
     try:
         from druglib.models.builder import INTERACTION  # type: ignore
         from druglib.models.Docking.default_MLDockBuilder import MLDOCK_BUILDER  # type: ignore

@@ -42,9 +42,14 @@ def pack_records(ids: Sequence[int], ligs: Sequence[torch.Tensor], a14s: Sequenc
     return rec
 
 
-def unpack_records(rec: torch.Tensor, max_nl: int, with_scores: bool = False):
+def unpack_records(rec: torch.Tensor, max_nl: int, with_scores: Optional[bool] = None):
+    """``with_scores=None``: decided from the records themselves (any non-NaN score field), i.e. identically on every rank."""
     out = {}
-    for r in rec.reshape(-1, rec.shape[-1]):
+    flat = rec.reshape(-1, rec.shape[-1])
+    if with_scores is None:
+        valid = flat[:, 0] >= 0
+        with_scores = bool((valid & ~torch.isnan(flat[:, 3])).any())
+    for r in flat:
         i = int(r[0].item())
         if i < 0:
             continue
@@ -61,10 +66,11 @@ def gather_poses(ids, ligs, a14s, n_samples: int, max_nl: int, max_nr: int, grou
     n_slots = (n_samples + world - 1) // world
     rec = pack_records(ids, ligs, a14s, max_nl, max_nr, n_slots, device, scores)
     if world == 1:
-        return unpack_records(rec, max_nl, scores is not None)
+        return unpack_records(rec, max_nl)
     out = [torch.empty_like(rec) for _ in range(world)]
     dist.all_gather(out, rec, group=group)
-    return unpack_records(torch.stack(out).cpu(), max_nl, scores is not None)
+    # whether the records carry scores is read off the gathered records (a rank without local samples has no opinion)
+    return unpack_records(torch.stack(out).cpu(), max_nl)
 
 
 def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], List[Tuple[torch.Tensor, torch.Tensor]]],
@@ -78,13 +84,17 @@ def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], List[
     ids, ligs, a14s, scores = [], [], [], []
     for chunk in batches(mine, batch_size):
         res = run_batch([samples[i] for i in chunk])
+        if len(res) != len(chunk):
+            raise RuntimeError(f"run_batch returned {len(res)} results for {len(chunk)} samples")
         for i, r in zip(chunk, res):
             ids.append(i); ligs.append(r[0]); a14s.append(r[1])
             if len(r) > 2:
                 scores.append(float(r[2]))
+    if scores and len(scores) != len(ids):
+        raise RuntimeError("run_batch returned a mix of scored and unscored samples")
     max_nl = max(int(s["lig_pos"].shape[0]) for s in samples)
     max_nr = max(int(s["sequence"].shape[0]) for s in samples)
-    return gather_poses(ids, ligs, a14s, len(samples), max_nl, max_nr, group, device, scores if len(scores) == len(ids) and ids else None)
+    return gather_poses(ids, ligs, a14s, len(samples), max_nl, max_nr, group, device, scores if scores else None)
 
 
 def slice_noise(noise: Sequence[Dict[str, torch.Tensor]], graphs: Sequence[int], tor_per_graph: Sequence[int],

@@ -318,3 +318,31 @@ def hetero_from_flat(x: Dict[str, torch.Tensor]) -> HeteroData:
     l = d[("ligand", "l2l", "ligand")]
     l.edge_index, l.edge_s = x["lig_edge_index"], x["lig_edge_s"]
     return d
+
+
+def install_real_registry(root: str = "/root/reference"):
+    """Replace the stand-in registries of ``install()`` by the reference's REAL registry machinery, executed unmodified from
+    the read-only tree: ``druglib/utils/registry.py`` (``Registry``, ``build_from_cfg``), ``druglib/models/base_model_builder.py``,
+    ``druglib/models/builder.py`` (``build_task_model``, ``INTERACTION``, ``MLDOCK_BUILDER``, ``TASKS_MANAGER`` ...) and
+    ``druglib/models/Docking/default_MLDockBuilder.py``.  ``druglib.utils.Config`` (mmcv-style, needs addict/yapf) is only used
+    as a type annotation by those files and is served as ``dict``.  Returns the real ``druglib.models.builder`` module."""
+    install(root)
+    import importlib.util
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, *rel.split("/")))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        parent, child = name.rsplit(".", 1)
+        setattr(sys.modules[parent], child, m)
+        return m
+
+    load("druglib.utils.misc", "druglib/utils/misc.py")
+    reg = load("druglib.utils.registry", "druglib/utils/registry.py")
+    utils = sys.modules["druglib.utils"]
+    utils.Registry, utils.build_from_cfg, utils.Config = reg.Registry, reg.build_from_cfg, dict
+    load("druglib.models.base_model_builder", "druglib/models/base_model_builder.py")
+    builder = load("druglib.models.builder", "druglib/models/builder.py")
+    load("druglib.models.Docking.default_MLDockBuilder", "druglib/models/Docking/default_MLDockBuilder.py")
+    return builder

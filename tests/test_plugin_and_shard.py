@@ -26,6 +26,56 @@ def test_plugin_state_dict_matches_reference_contract():
         m.load_state_dict({k: v for k, v in sd.items() if "tr_final_layer" not in k}, strict=True)
 
 
+def _reference_checkpoint_load(module, state_dict, strict=True):
+    """``load_state_dict`` of druglib/core/runner/checkpoint.py:32-100 restated: recursion over ``module._modules`` calling
+    ``_load_from_state_dict(state_dict, prefix, {}, True, missing, unexpected, err)`` on ONE shared copy of the state dict; raises
+    like the reference when ``strict`` and anything is missing / unexpected."""
+    unexpected, missing, err = [], [], []
+    sd = state_dict.copy()
+
+    def load(m, prefix=""):
+        m._load_from_state_dict(sd, prefix, {}, True, missing, unexpected, err)
+        for name, child in m._modules.items():
+            if child is not None:
+                load(child, prefix + name + ".")
+
+    load(module)
+    missing = [k for k in missing if "num_batches_tracked" not in k]
+    if unexpected:
+        err.append("unexpected key in source state_dict: " + ", ".join(unexpected))
+    if missing:
+        err.append("missing keys in source state_dict: " + ", ".join(missing))
+    if err and strict:
+        raise RuntimeError("The model and loaded state dict do not match exactly\n" + "\n".join(err))
+    return missing, unexpected
+
+
+def test_plugin_loads_through_the_reference_checkpoint_loader_strict():
+    """predict.py:118-125 loads with the reference's own loader (strict=True) from the TOP-LEVEL model; the e3nn
+    ``*.tp.*`` / ``final_tp_tor.*`` buffers of a shipped checkpoint must be tolerated there too, and a reload must invalidate the
+    packed device weights."""
+    top = plugin.DiffBindFR(diffusion_model=dict(cfg=None))
+    sd = {"diffusion_model." + k: v for k, v in weights.random_state_dict(5).items()}
+    sd["diffusion_model.lig_conv_layers.0.tp.output_mask"] = torch.ones(84)
+    sd["diffusion_model.lig_conv_layers.0.tp.weight"] = torch.empty(0)
+    sd["diffusion_model.cross_la_conv_layers.4.tp._w3j_1_1_1"] = torch.zeros(3, 3, 3)
+    sd["diffusion_model.final_tp_tor.output_mask"] = torch.ones(45)
+    top.diffusion_model._packed = True                      # as after a first engine() call
+    missing, unexpected = _reference_checkpoint_load(top, sd, strict=True)
+    assert not missing and not unexpected
+    assert top.diffusion_model._packed is False
+    got = top.state_dict()
+    assert torch.equal(got["diffusion_model.atom_conv_layers.2.fc.lin.3.weight"], sd["diffusion_model.atom_conv_layers.2.fc.lin.3.weight"])
+    res = top.load_state_dict(sd, strict=True)                # torch's loader from the top level as well
+    assert not res.missing_keys and not res.unexpected_keys
+    bad = dict(sd); bad["diffusion_model.not_a_module.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        _reference_checkpoint_load(top, bad, strict=True)
+    short = {k: v for k, v in sd.items() if "rot_final_layer" not in k}
+    with pytest.raises(RuntimeError):
+        _reference_checkpoint_load(top, short, strict=True)
+
+
 def test_plugin_rejects_unsupported_architecture():
     with pytest.raises(NotImplementedError):
         plugin.TensorProductModel(dict(ns=32))
@@ -54,6 +104,48 @@ def test_plugin_registers_in_reference_registries():
     from druglib.models.Docking.default_MLDockBuilder import MLDOCK_BUILDER
     assert INTERACTION.module_dict["TensorProductModelB200"] is plugin.TensorProductModel
     assert MLDOCK_BUILDER.module_dict["DiffBindFRB200"] is plugin.DiffBindFR
+
+
+@pytest.mark.reference
+def test_plugin_is_built_by_the_reference_build_task_model():
+    """``build_task_model`` (druglib/models/builder.py:52-79) -> ``DefaultMLDOCKBuilder.build_model``
+    (default_MLDockBuilder.py:8-27) -> ``MLDOCK_BUILDER.build`` must hand back the plugin when the config selects it, with the
+    reference's ``model`` section otherwise unchanged (``task``, ``diffusion_model.cfg``, ``test_cfg``)."""
+    from oracle import shims
+    builder = shims.install_real_registry()               # the reference's real Registry / builder files, unmodified
+    assert plugin.register()
+    build_task_model = builder.build_task_model
+    assert builder.INTERACTION.get("TensorProductModelB200") is plugin.TensorProductModel
+    assert builder.MLDOCK_BUILDER.get("DiffBindFRB200") is plugin.DiffBindFR
+    cfg = shims.EasyDict(task="mldock", type="DiffBindFRB200",
+                         diffusion_model=shims.EasyDict(type="TensorProductModelB200", cfg=shims.reference_model_cfg(), conv_kernel=5),
+                         test_cfg=shims.EasyDict(sample_cfg=shims.reference_sample_cfg()))
+    model = build_task_model(cfg)
+    assert isinstance(model, plugin.DiffBindFR) and isinstance(model.diffusion_model, plugin.TensorProductModel)
+    assert model.diffusion_model.conv_kernel == 5
+    assert model.sample_cfg().actual_steps == 20 and model.sample_cfg().inference_steps == 22
+    keys = set(model.state_dict().keys())
+    assert "diffusion_model.lig_conv_layers.3.fc.lin.3.weight" in keys
+
+
+def test_register_rebinds_the_mdn_scorer_class():
+    """``common.engines.Scorer`` builds whatever the name ``KarmaDock`` of its module is bound to
+    (DiffBindFR/common/engines.py:29-31,246); ``register()`` rebinds it, so the rescoring stage needs no source edit."""
+    import sys
+    import types
+    pkg, common, eng = types.ModuleType("DiffBindFR"), types.ModuleType("DiffBindFR.common"), types.ModuleType("DiffBindFR.common.engines")
+    eng.KarmaDock = object
+    saved = {k: sys.modules.get(k) for k in ("DiffBindFR", "DiffBindFR.common", "DiffBindFR.common.engines")}
+    sys.modules.update({"DiffBindFR": pkg, "DiffBindFR.common": common, "DiffBindFR.common.engines": eng})
+    try:
+        assert plugin.rebind_scorer()
+        assert eng.KarmaDock is plugin.KarmaDock
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
 
 
 def test_forward_without_cuda_fails_loudly():
@@ -93,6 +185,11 @@ def _worker(rank, world, port, q):
     got = shard.run_sharded(samples, lambda ch: [(a, b, float(a.sum())) for a, b in run_batch(ch)], batch_size=3)
     for i, s in enumerate(samples):
         ok &= abs(got[i][2] - float((torch.from_numpy(s["lig_pos"]) * 2 + 1).sum())) < 1e-3
+    # fewer samples than ranks: the rank without local work must still see the scores of the others
+    got = shard.run_sharded(samples[:1], lambda ch: [(a, b, 1.5) for a, b in run_batch(ch)], batch_size=2)
+    ok &= sorted(got) == [0] and len(got[0]) == 3 and abs(got[0][2] - 1.5) < 1e-6
+    got = shard.run_sharded(samples[:1], run_batch, batch_size=2)            # and without scores: 2-tuples everywhere
+    ok &= len(got[0]) == 2
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

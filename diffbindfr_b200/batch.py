@@ -76,9 +76,15 @@ def prepare(batch: Dict[str, object]) -> Dict[str, np.ndarray]:
     sc_graph = ab[sc_bonds[:, 0]] if n_sc else np.zeros(0, dtype=np.int64)
     assert n_sc == 0 or np.all(np.diff(sc_graph) >= 0), "chi bonds must be grouped by graph"
     sc_ptr = np.concatenate([[0], np.cumsum(np.bincount(sc_graph, minlength=B))]).astype(np.int32)
-    res_graph = ab[np.searchsorted(np.cumsum(amask.sum(1)), np.arange(N_r), side="right").clip(max=N_a - 1)] if N_a else np.zeros(N_r, np.int64)
-    # residues without atoms inherit the graph of the next atom; res_ptr only used for bookkeeping
-    res_ptr = np.concatenate([[0], np.cumsum(np.bincount(res_graph, minlength=B))]).astype(np.int32)
+    if "res_ptr" in batch and batch["res_ptr"] is not None:
+        res_ptr = _np(batch["res_ptr"], np.int64).astype(np.int32)          # collated batches carry it (synth.collate)
+    else:
+        # graph of a residue = graph of its first atom; residues without atoms inherit the graph of the next atom
+        per_res = amask.sum(1).astype(np.int64)
+        first_atom = np.concatenate([[0], np.cumsum(per_res)[:-1]]).clip(max=max(N_a - 1, 0))
+        res_graph = ab[first_atom] if N_a else np.zeros(N_r, np.int64)
+        res_ptr = np.concatenate([[0], np.cumsum(np.bincount(res_graph, minlength=B))]).astype(np.int32)
+    assert len(res_ptr) == B + 1 and int(res_ptr[-1]) == N_r, "res_ptr must cover every residue"
     out = dict(
         lig_node=_np(batch["lig_node"], np.float32), lig_pos=_np(batch["lig_pos"], np.float32),
         lig_ptr=lig_ptr, lig_batch=lb.astype(np.int32), bond_ptr=bond_ptr,

@@ -20,6 +20,8 @@
 #include "pose.cuh"
 #include "mdn.cuh"
 #include "mdn_enc.cuh"
+#include "mdn_feat.cuh"
+#include "assemble.cuh"
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -87,7 +89,8 @@ struct B200Handle {
   int tp_grid = 148;
   std::vector<float> cg_dense; int atom14_group[21 * 14];
   // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
-  int* host_meta = nullptr; bool deferred_check = false;
+  int* host_meta = nullptr; bool deferred_check = false; size_t feat_smem = 48 * 1024;
+  Buf ex_in, ex_pin, ex_out[32];   // batch assembly: staged base batch (device / pinned) and the expanded arrays
   Buf trace; bool trace_on = false;
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool use_side = true;
 };
@@ -578,6 +581,9 @@ void b200dock_destroy(B200Handle* h) {
   if (h->pinned_in.p) cudaFreeHost(h->pinned_in.p);
   if (h->pinned_out.p) cudaFreeHost(h->pinned_out.p);
   if (h->host_meta) cudaFreeHost(h->host_meta);
+  if (h->ex_pin.p) cudaFreeHost(h->ex_pin.p);
+  if (h->ex_in.p) cudaFree(h->ex_in.p);
+  for (auto& b : h->ex_out) if (b.p) cudaFree(b.p);
   for (void* p : h->plan_allocs) cudaFree(p);
   if (h->d_blob) cudaFree(h->d_blob);
   if (h->d_w16) cudaFree(h->d_w16);
@@ -923,6 +929,173 @@ int b200dock_mdn_encode(B200Handle* h, const B200MdnGraph* g, float* pro_s, floa
   { GvpLnArgs L{}; L.rows = g->N_r; L.ns = 128; L.nv = 16; L.s = s; L.v = v; L.out_s = sb; L.out_v = vb; C.ln(L, 173); }
   C.gvp(gvp_plain(g->N_r, 128, 16, 128, 0, sb, vb, pro_s, nullptr), 175, 1, 0);
   CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200dock_mdn_featurize(B200Handle* h, const B200MdnFeat* f, void* stream) {
+  if (!h || !f) return B200_ERR_INVALID;
+  if (f->B <= 0 || f->N_r <= 0 || f->topk <= 0 || f->topk > 32 || f->max_res <= 0) FAIL(B200_ERR_INVALID, "bad MDN featuriser sizes (topk must be 1..32)");
+  const size_t smem = (size_t)f->max_res * (3 * 8 + 6 * 4) + 8 * 32 * 4;
+  if (smem > 220 * 1024) FAIL(B200_ERR_INVALID, "pocket too large for the MDN featuriser (more than ~4600 residues)");
+  CK(cudaSetDevice(h->device));
+  if (smem > h->feat_smem) {
+    CK(cudaFuncSetAttribute(k_mdn_featurize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->feat_smem = smem;
+  }
+  MdnFeatArgs A{};
+  A.B = f->B; A.topk = f->topk; A.res_ptr = f->res_ptr; A.edge_ptr = (const long long*)f->edge_ptr;
+  A.atom14 = f->atom14; A.mask = f->atom14_mask; A.bb_sincos = f->bb_sincos;
+  A.node_s = f->node_s; A.node_v = f->node_v; A.edge_src = f->edge_src; A.edge_dst = f->edge_dst;
+  A.edge_s = f->edge_s; A.edge_v = f->edge_v; A.node_ptr = f->node_ptr;
+  k_mdn_featurize<<<f->B, 256, smem, (cudaStream_t)stream>>>(A);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200dock_expand_host(B200Handle* h, const B200Batch* base, const B200Expand* ex, B200Batch* out, void* stream) {
+  if (!h || !base || !ex || !out || !ex->src_graph || ex->B_out <= 0) return B200_ERR_INVALID;
+  if (ex->randomize && !ex->stream_id) FAIL(B200_ERR_INVALID, "randomize needs one RNG stream id per output graph");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const B200Batch& b = *base;
+  const int Bo = ex->B_out;
+  for (int g = 0; g < Bo; ++g)
+    if (ex->src_graph[g] < 0 || ex->src_graph[g] >= b.B) FAIL(B200_ERR_INVALID, "src_graph out of range");
+  // ---- per-entity offsets of the base graphs (host arrays are readable here)
+  enum { EL, EE, ET, EM, EA, ER, ER14, ES, NENT };
+  std::vector<long long> off[NENT];
+  for (auto& v : off) v.assign(b.B + 1, 0);
+  for (int g = 0; g <= b.B; ++g) {
+    off[EL][g] = b.lig_ptr[g]; off[EE][g] = b.bond_ptr[b.lig_ptr[g]]; off[ET][g] = b.tor_ptr[g];
+    off[EA][g] = b.atom_ptr[g]; off[ER][g] = b.res_ptr[g]; off[ER14][g] = 14LL * b.res_ptr[g]; off[ES][g] = b.sc_ptr[g];
+  }
+  for (int g = 0; g < b.B; ++g)
+    off[EM][g + 1] = off[EM][g] + (long long)(b.tor_ptr[g + 1] - b.tor_ptr[g]) * (b.lig_ptr[g + 1] - b.lig_ptr[g]);
+  // ---- small per-output-graph tables: new_ptr [Bo+1], old_start [Bo], delta [Bo] per entity, + int64 delta of the mask offsets
+  const size_t per = (size_t)(Bo + 1) + 2 * (size_t)Bo;
+  std::vector<int> tab(NENT * per);
+  std::vector<long long> d64(Bo);
+  long long tot[NENT];
+  for (int e = 0; e < NENT; ++e) {
+    int* np = tab.data() + e * per; int* os = np + Bo + 1; int* dl = os + Bo;
+    long long run = 0;
+    for (int g = 0; g < Bo; ++g) {
+      const int sg = ex->src_graph[g];
+      np[g] = (int)run; os[g] = (int)off[e][sg]; dl[g] = (int)(run - off[e][sg]);
+      if (e == EM) d64[g] = run - off[e][sg];
+      run += off[e][sg + 1] - off[e][sg];
+    }
+    np[Bo] = (int)run; tot[e] = run;
+    if (run > 0x7fffffffLL) FAIL(B200_ERR_INVALID, "expanded batch too large for 32-bit indices");
+  }
+  B200Batch o{};
+  o.B = Bo; o.N_l = (int)tot[EL]; o.E_b = (int)tot[EE]; o.n_tor = (int)tot[ET]; o.N_a = (int)tot[EA]; o.N_r = (int)tot[ER]; o.n_sc = (int)tot[ES];
+  o.rot_mask_bytes = tot[EM];
+  o.max_lig_atoms = 0; o.cross_pairs = 0; o.atom_pairs = 0;
+  for (int g = 0; g < Bo; ++g) {
+    const int sg = ex->src_graph[g];
+    const long long nl = b.lig_ptr[sg + 1] - b.lig_ptr[sg], na = b.atom_ptr[sg + 1] - b.atom_ptr[sg];
+    o.max_lig_atoms = std::max<int>(o.max_lig_atoms, (int)nl);
+    o.cross_pairs += nl * na; o.atom_pairs += na * na;
+  }
+  if (o.max_lig_atoms > POSE_MAX_ATOMS) FAIL(B200_ERR_INVALID, "ligand larger than 256 heavy atoms is not supported");
+  // ---- stage the base batch + tables through one pinned arena, one H2D copy
+  struct Item { const void* src; size_t bytes; size_t offp; };
+  std::vector<Item> items;
+  size_t total = 0;
+  auto add = [&](const void* p, size_t bytes) { size_t ofs = total; items.push_back({p, bytes, ofs}); total += (bytes + 255) & ~(size_t)255; return ofs; };
+  const int one_past = (int)tot[EE];
+  const size_t i_lig_node = add(b.lig_node, (size_t)b.N_l * 108), i_lig_pos = add(b.lig_pos, (size_t)b.N_l * 12),
+               i_bond_ptr = add(b.bond_ptr, (size_t)(b.N_l + 1) * 4), i_bond_dst = add(b.bond_dst, (size_t)b.E_b * 4),
+               i_bond_eid = add(b.bond_eid, (size_t)b.E_b * 4), i_ef = add(b.lig_edge_feat, (size_t)b.E_b * 40),
+               i_tb = add(b.tor_bonds, (size_t)b.n_tor * 8), i_rm = add(b.rot_mask, (size_t)b.rot_mask_bytes),
+               i_rmo = add(b.rot_mask_off, (size_t)b.n_tor * 8), i_pf = add(b.pocket_feat, (size_t)b.N_a * 20),
+               i_rp = add(b.rec_atm_pos, (size_t)b.N_a * 12), i_as = add(b.atom_slot, (size_t)b.N_a * 4),
+               i_m14 = add(b.atom14_mask, (size_t)b.N_r * 14), i_seq = add(b.sequence, (size_t)b.N_r * 4),
+               i_bt = add(b.backbone_transl, (size_t)b.N_r * 12), i_bR = add(b.backbone_rots, (size_t)b.N_r * 36),
+               i_df = add(b.default_frame, (size_t)b.N_r * 512), i_rg = add(b.rigid_group_pos, (size_t)b.N_r * 168),
+               i_ta = add(b.torsion_angle, (size_t)b.N_r * 20), i_scb = add(b.sc_bonds, (size_t)b.n_sc * 8),
+               i_sci = add(b.sc_index, (size_t)b.N_r * 16), i_tab = add(tab.data(), tab.size() * 4), i_d64 = add(d64.data(), d64.size() * 8),
+               i_sid = add(ex->stream_id, ex->stream_id ? (size_t)Bo * 8 : 0), i_last = add(&one_past, 4);
+  if (total > h->ex_pin.cap) {
+    if (h->ex_pin.p) CK(cudaFreeHost(h->ex_pin.p));
+    h->ex_pin.p = nullptr; h->ex_pin.cap = 0;
+    CK(cudaMallocHost(&h->ex_pin.p, total + total / 8));
+    h->ex_pin.cap = total + total / 8;
+  }
+  ENS(h->ex_in, total);
+  char* pin = (char*)h->ex_pin.p;
+  for (const Item& it : items) if (it.bytes) memcpy(pin + it.offp, it.src, it.bytes);
+  CK(cudaMemcpyAsync(h->ex_in.p, pin, total, cudaMemcpyHostToDevice, st));
+  const char* d = (const char*)h->ex_in.p;
+  auto tabp = [&](int e, int which) { return reinterpret_cast<const int*>(d + i_tab) + e * per + (which == 0 ? 0 : (which == 1 ? Bo + 1 : 2 * Bo + 1)); };
+  // ---- output arrays
+  int slot = 0;
+  auto outbuf = [&](size_t bytes) -> void* { Buf& bf = h->ex_out[slot++]; if (ensure(h, bf, bytes ? bytes : 4)) return nullptr; return bf.p; };
+  ExpandLaunch L{};
+  L.B_out = Bo;
+  bool alloc_fail = false;
+  auto job = [&](const void* src, size_t row_bytes, int ent, int fix_ent, unsigned fix_mask, int set_graph, bool bytes_mode, bool is64) -> void* {
+    const long long rows = bytes_mode ? tot[ent] : tot[ent];
+    void* dst = outbuf((size_t)rows * (bytes_mode ? 1 : row_bytes) + 16);
+    if (!dst) { alloc_fail = true; return nullptr; }
+    ExpandJob& J = L.j[L.n++];
+    J.src = src; J.dst = dst; J.words = bytes_mode ? 1 : (int)(row_bytes / 4); J.byte_rows = bytes_mode ? 1 : 0;
+    J.new_ptr = tabp(ent, 0); J.old_start = tabp(ent, 1);
+    J.delta = fix_ent >= 0 ? tabp(fix_ent, 2) : nullptr;
+    J.delta64 = is64 ? reinterpret_cast<const long long*>(d + i_d64) : nullptr;
+    J.fix_mask = fix_mask; J.set_graph = set_graph; J.n_rows = (int)rows;
+    return dst;
+  };
+  o.lig_node = (const float*)job(d + i_lig_node, 108, EL, -1, 0, 0, false, false);
+  o.lig_pos = (float*)job(d + i_lig_pos, 12, EL, -1, 0, 0, false, false);
+  o.lig_batch = (const int*)job(nullptr, 4, EL, -1, 0, 1, false, false);
+  o.bond_ptr = (const int*)job(d + i_bond_ptr, 4, EL, EE, 1u, 0, false, false);
+  o.bond_dst = (const int*)job(d + i_bond_dst, 4, EE, EL, 1u, 0, false, false);
+  o.bond_eid = (const int*)job(d + i_bond_eid, 4, EE, EE, 1u, 0, false, false);
+  o.lig_edge_feat = (const float*)job(d + i_ef, 40, EE, -1, 0, 0, false, false);
+  o.tor_bonds = (const int*)job(d + i_tb, 8, ET, EL, 3u, 0, false, false);
+  o.rot_mask_off = (const int64_t*)job(d + i_rmo, 8, ET, -1, 0, 0, false, true);
+  o.rot_mask = (const uint8_t*)job(d + i_rm, 1, EM, -1, 0, 0, true, false);
+  o.pocket_feat = (const int*)job(d + i_pf, 20, EA, -1, 0, 0, false, false);
+  o.rec_atm_pos = (float*)job(d + i_rp, 12, EA, -1, 0, 0, false, false);
+  o.atom_batch = (const int*)job(nullptr, 4, EA, -1, 0, 1, false, false);
+  o.atom_slot = (const int*)job(d + i_as, 4, EA, ER14, 1u, 0, false, false);
+  o.atom14_mask = (const uint8_t*)job(d + i_m14, 1, ER14, -1, 0, 0, true, false);
+  o.sequence = (const int*)job(d + i_seq, 4, ER, -1, 0, 0, false, false);
+  o.backbone_transl = (const float*)job(d + i_bt, 12, ER, -1, 0, 0, false, false);
+  o.backbone_rots = (const float*)job(d + i_bR, 36, ER, -1, 0, 0, false, false);
+  o.default_frame = (const float*)job(d + i_df, 512, ER, -1, 0, 0, false, false);
+  o.rigid_group_pos = (const float*)job(d + i_rg, 168, ER, -1, 0, 0, false, false);
+  o.torsion_angle = (float*)job(d + i_ta, 20, ER, -1, 0, 0, false, false);
+  o.sc_index = (const int*)job(d + i_sci, 16, ER, ES, 15u, 0, false, false);
+  o.sc_bonds = (const int*)job(d + i_scb, 8, ES, EA, 3u, 0, false, false);
+  if (alloc_fail) return B200_ERR_CUDA;
+  o.lig_ptr = tabp(EL, 0); o.tor_ptr = tabp(ET, 0); o.atom_ptr = tabp(EA, 0); o.res_ptr = tabp(ER, 0); o.sc_ptr = tabp(ES, 0);
+  k_expand<<<dim3(148 * 2, L.n), 256, 0, st>>>(L);
+  CK(cudaMemcpyAsync(const_cast<int*>(o.bond_ptr) + o.N_l, d + i_last, 4, cudaMemcpyDeviceToDevice, st));   // CSR end
+  h->launches = 1;
+  if (ex->randomize) {
+    const unsigned long long* sid = reinterpret_cast<const unsigned long long*>(d + i_sid);
+    LigInitArgs LA{Bo, o.lig_pos, o.lig_ptr, o.tor_bonds, o.tor_ptr, o.rot_mask, (const long long*)o.rot_mask_off, sid,
+                   (unsigned long long)ex->seed, ex->tr_sigma_max};
+    k_lig_init<<<Bo, 32, 0, st>>>(LA);
+    ChiInitArgs CA{o.N_r, Bo, o.res_ptr, o.torsion_angle, o.sc_index, sid, (unsigned long long)ex->seed};
+    k_chi_init<<<cdiv(o.N_r, 128), 128, 0, st>>>(CA);
+    // atom14 / rec_atm_pos from the new chi angles (build_pdb_from_template, prot_math.py:243-291)
+    ENS(h->atom14, (size_t)o.N_r * 42 * 4);
+    SideChainArgs S{};
+    S.N_r = o.N_r; S.N_a = o.N_a; S.sequence = o.sequence; S.bb_t = o.backbone_transl; S.bb_R = o.backbone_rots;
+    S.default_frame = o.default_frame; S.rigid_pos = o.rigid_group_pos; S.torsion_angle = o.torsion_angle;
+    S.sc_index = o.sc_index; S.atom14_mask = o.atom14_mask; S.atom_slot = o.atom_slot; S.apply_update = 0;
+    S.atom14 = h->atom14.as<float>();
+    k_sidechain_update<<<cdiv(o.N_r, 64), 64, 0, st>>>(S);
+    k_gather_atoms<<<grid_for(o.N_a, 256, 148 * 4), 256, 0, st>>>(S.atom14, o.atom_slot, o.N_a, o.rec_atm_pos);
+    h->launches += 4;
+  }
+  CK(cudaGetLastError());
+  *out = o;
   return B200_OK;
 }
 

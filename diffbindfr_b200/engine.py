@@ -22,11 +22,11 @@ _lib = None
 
 EXPORTS = ["b200dock_create", "b200dock_destroy", "b200dock_last_error", "b200dock_version",
            "b200dock_load_weights", "b200dock_score", "b200dock_sample", "b200dock_sample_host",
-           "b200dock_set_deferred_check", "b200dock_check",
+           "b200dock_set_deferred_check", "b200dock_check", "b200dock_expand_host",
            "b200dock_last_edge_counts", "b200dock_last_launch_count", "b200dock_set_profiling",
            "b200dock_tp_kernel_time_ms", "b200dock_debug_tap", "b200dock_debug_set",
            "b200dock_mdn_load_weights", "b200dock_mdn_score",
-           "b200dock_mdn_load_encoder_weights", "b200dock_mdn_encode"]
+           "b200dock_mdn_load_encoder_weights", "b200dock_mdn_encode", "b200dock_mdn_featurize"]
 
 
 class CCond(C.Structure):
@@ -38,6 +38,18 @@ class CStep(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("t", "dt", "tr_sigma", "rot_score_norm", "tor_score_norm2",
                                          "sc_tor_score_norm2", "tr_g2", "tr_gs", "rot_g2", "rot_gs", "tor_g2", "tor_gs",
                                          "sc_g2", "sc_gs")] + [("ode", C.c_int32), ("reserved", C.c_int32)]
+
+
+class CExpand(C.Structure):
+    _fields_ = [("B_out", C.c_int32), ("randomize", C.c_int32), ("src_graph", C.c_void_p), ("stream_id", C.c_void_p),
+                ("seed", C.c_uint64), ("tr_sigma_max", C.c_float), ("reserved", C.c_float)]
+
+
+class _DevArray:
+    """Zero-copy torch view of a device buffer owned by the library (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
 
 
 def load_library(path: Optional[str] = None):
@@ -61,6 +73,7 @@ def load_library(path: Optional[str] = None):
         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]
     lib.b200dock_set_deferred_check.argtypes = [C.c_void_p, C.c_int]
     lib.b200dock_check.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200dock_expand_host.argtypes = [C.c_void_p, C.POINTER(batch_mod.CBatch), C.POINTER(CExpand), C.POINTER(batch_mod.CBatch), C.c_void_p]
     lib.b200dock_last_edge_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.b200dock_last_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.b200dock_set_profiling.argtypes = [C.c_void_p, C.c_int]
@@ -71,6 +84,7 @@ def load_library(path: Optional[str] = None):
     lib.b200dock_mdn_score.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
     lib.b200dock_mdn_load_encoder_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
     lib.b200dock_mdn_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.b200dock_mdn_featurize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -229,6 +243,51 @@ class Engine:
                                            lig.ctypes.data, a14.ctypes.data, C.byref(h2d), C.byref(d2h), st)
         self._check(rc)
         return torch.from_numpy(lig), torch.from_numpy(a14), int(h2d.value), int(d2h.value)
+
+    # ------------------------------------------------------- batch assembly on the device
+    def expand(self, arrs: Dict[str, object], src_graph: Sequence[int], stream_ids: Optional[Sequence[int]] = None, seed: int = 0,
+               tr_sigma_max: float = 10.0, randomize: bool = True):
+        """``arrs`` = ``batch.prepare`` of a batch holding every COMPLEX once (host arrays); returns a device-resident batch whose
+        graph g is a copy of complex ``src_graph[g]`` with - when ``randomize`` - a fresh LigInit / SCProtInit starting pose
+        drawn from the Philox stream (seed, stream_ids[g]) (struct_init.py:16-53,113-136 on the device).  The returned
+        ``CBatch`` holds device pointers owned by the library until the next ``expand``."""
+        src = np.ascontiguousarray(np.asarray(src_graph, dtype=np.int32))
+        sid = np.ascontiguousarray(np.asarray(stream_ids if stream_ids is not None else np.arange(len(src)), dtype=np.uint64))
+        assert len(sid) == len(src)
+        cb = batch_mod.to_struct(arrs, {f: arrs[f].ctypes.data for f in batch_mod.POINTER_FIELDS})
+        ex = CExpand(len(src), 1 if randomize else 0, src.ctypes.data, sid.ctypes.data, int(seed), float(tr_sigma_max), 0.0)
+        out = batch_mod.CBatch()
+        st = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+        self._check(self.lib.b200dock_expand_host(self.h, C.byref(cb), C.byref(ex), C.byref(out), st))
+        self._keep_expand = (src, sid)
+        return out
+
+    def view(self, cb, field: str) -> torch.Tensor:
+        """Zero-copy tensor view of an array of an expanded batch."""
+        dev = torch.device("cuda", self.device)
+        shapes = dict(lig_pos=((cb.N_l, 3), "<f4"), rec_atm_pos=((cb.N_a, 3), "<f4"), torsion_angle=((cb.N_r, 5), "<f4"),
+                      lig_ptr=((cb.B + 1,), "<i4"), atom_ptr=((cb.B + 1,), "<i4"), res_ptr=((cb.B + 1,), "<i4"), tor_ptr=((cb.B + 1,), "<i4"),
+                      sc_ptr=((cb.B + 1,), "<i4"), lig_batch=((cb.N_l,), "<i4"), atom_batch=((cb.N_a,), "<i4"), tor_bonds=((max(cb.n_tor, 1), 2), "<i4"),
+                      sc_bonds=((max(cb.n_sc, 1), 2), "<i4"), bond_ptr=((cb.N_l + 1,), "<i4"), bond_dst=((max(cb.E_b, 1),), "<i4"),
+                      bond_eid=((max(cb.E_b, 1),), "<i4"), atom_slot=((cb.N_a,), "<i4"), sc_index=((cb.N_r, 4), "<i4"), sequence=((cb.N_r,), "<i4"),
+                      atom14_mask=((cb.N_r, 14), "|u1"), lig_node=((cb.N_l, 27), "<f4"), pocket_feat=((cb.N_a, 5), "<i4"),
+                      default_frame=((cb.N_r, 8, 4, 4), "<f4"), rot_mask=((max(int(cb.rot_mask_bytes), 1),), "|u1"),
+                      rot_mask_off=((max(cb.n_tor, 1),), "<i8"), lig_edge_feat=((max(cb.E_b, 1), 10), "<f4"))
+        shape, ts = shapes[field]
+        return torch.as_tensor(_DevArray(getattr(cb, field), shape, ts), device=dev)
+
+    def sample_expanded(self, cb, steps: Sequence[StepScalars], noise: torch.Tensor, ode: bool = False):
+        """``b200dock_sample`` on a batch produced by ``expand``; returns (lig_pos view (N_l,3), atom14 (N_r,14,3))."""
+        dev = torch.device("cuda", self.device)
+        csteps = steps_to_c(steps, ode)
+        temb = sinusoidal_embedding(torch.tensor([s.t for s in steps], dtype=torch.float32)).contiguous()
+        noise_d = noise.to(dev).contiguous()
+        a14 = torch.empty(cb.N_r, 14, 3, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._keep = [noise_d, temb, csteps]
+        self._check(self.lib.b200dock_sample(self.h, C.byref(cb), csteps, len(steps), temb.data_ptr(), noise_d.data_ptr(), None,
+                                             a14.data_ptr(), None, st))
+        return self.view(cb, "lig_pos"), a14
 
     # ------------------------------------------------------------ introspection
     def edge_counts(self) -> Dict[str, int]:

@@ -24,6 +24,12 @@ class CMdnBatch(C.Structure):
         (n, C.c_void_p) for n in ("lig_s", "lig_pos", "lig_ptr", "pro_s", "xyz_full", "res_ptr")]
 
 
+class CMdnFeat(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "N_r", "topk", "max_res")] + [("E", C.c_int64)] + [
+        (n, C.c_void_p) for n in ("res_ptr", "edge_ptr", "atom14", "atom14_mask", "bb_sincos", "node_s", "node_v", "edge_src",
+                                  "edge_dst", "edge_s", "edge_v", "node_ptr")]
+
+
 class CMdnGraph(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("N_r", "E_p", "N_l", "E_l")] + [
         (n, C.c_void_p) for n in ("pro_node_s", "pro_node_v", "pro_seq", "pro_src", "pro_dst", "pro_edge_s", "pro_edge_v",
@@ -117,6 +123,34 @@ class MDNScorer:
     def _dev(self):
         return torch.device("cuda", self.eng.device)
 
+    # ---- protein featurisation on the device (protein_feature.py:170-217 + knn_graph), one graph per pose
+    def featurize(self, atom14: torch.Tensor, res_ptr, atom14_mask: torch.Tensor, bb_sincos: torch.Tensor, topk: int = 30) -> Dict[str, torch.Tensor]:
+        """``atom14`` (N_r,14,3) device tensor (the sampler's output), ``res_ptr`` (B+1,) residues per graph, ``atom14_mask`` (N_r,14),
+        ``bb_sincos`` (N_r,6).  Returns the ``pro_*`` part of the scorer's flat input dict, on the device, plus ``pro_node_ptr``
+        (CSR of the edges by centre; the edges are already grouped by centre so no sort is needed)."""
+        dev = self._dev()
+        rp = np.asarray(res_ptr.cpu() if torch.is_tensor(res_ptr) else res_ptr, dtype=np.int64)
+        n = np.diff(rp)
+        B, N_r = len(n), int(rp[-1])
+        kk = np.minimum(topk, np.maximum(n - 1, 0))
+        ep = np.concatenate([[0], np.cumsum(n * kk)]).astype(np.int64)
+        E = int(ep[-1])
+        a14 = atom14.float().contiguous().to(dev)
+        t = dict(res_ptr=torch.from_numpy(rp.astype(np.int32)).to(dev), edge_ptr=torch.from_numpy(ep).to(dev), atom14=a14,
+                 mask=atom14_mask.to(torch.uint8).contiguous().to(dev), bb=bb_sincos.float().contiguous().to(dev),
+                 node_s=torch.empty(N_r, 9, device=dev), node_v=torch.empty(N_r, 3, 3, device=dev),
+                 src=torch.empty(max(E, 1), dtype=torch.int32, device=dev), dst=torch.empty(max(E, 1), dtype=torch.int32, device=dev),
+                 edge_s=torch.empty(max(E, 1), 21, device=dev), edge_v=torch.empty(max(E, 1), 1, 3, device=dev),
+                 node_ptr=torch.empty(N_r + 1, dtype=torch.int32, device=dev))
+        f = CMdnFeat(B, N_r, int(topk), int(n.max()), E, *[t[k].data_ptr() for k in ("res_ptr", "edge_ptr", "atom14", "mask", "bb", "node_s",
+                                                                                       "node_v", "src", "dst", "edge_s", "edge_v", "node_ptr")])
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self.eng._check(self.eng.lib.b200dock_mdn_featurize(self.eng.h, C.byref(f), st))
+        self._keep3 = t
+        return dict(pro_node_s=t["node_s"], pro_node_v=t["node_v"], pro_edge_index=torch.stack([t["src"][:E], t["dst"][:E]]),
+                    pro_edge_s=t["edge_s"][:E], pro_edge_v=t["edge_v"][:E], pro_node_ptr=t["node_ptr"], xyz_full=a14,
+                    pro_batch=torch.repeat_interleave(torch.arange(B), torch.from_numpy(n)).to(dev))
+
     # ---- KarmaDock.encoding
     def encoding(self, data: Dict[str, torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
         dev = self._dev()
@@ -127,7 +161,10 @@ class MDNScorer:
         les = data["lig_edge_s"][m.to(data["lig_edge_s"].device)]
         pei = data["pro_edge_index"]
         N_r, N_l = data["pro_node_s"].shape[0], data["lig_node_s"].shape[0]
-        pperm, pptr = _csr(pei[1], N_r)
+        if data.get("pro_node_ptr") is not None:         # edges from featurize(): already grouped by centre
+            pperm, pptr = torch.arange(pei.shape[1], dtype=torch.int32, device=dev), data["pro_node_ptr"]
+        else:
+            pperm, pptr = _csr(pei[1], N_r)
         lperm, lptr = _csr(lei[1], N_l)
         t = [f(data["pro_node_s"]), f(data["pro_node_v"]), i(data["pro_seq"]), i(pei[0]), i(pei[1]), f(data["pro_edge_s"]), f(data["pro_edge_v"]),
              pperm.to(dev), pptr.to(dev), f(data["lig_node_s"]), f(les), i(lei[0]), i(lei[1]), lperm.to(dev), lptr.to(dev)]

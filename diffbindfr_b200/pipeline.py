@@ -1,22 +1,130 @@
-"""Sampler -> MDN rescoring on one device (BASELINE.json configs[2]: "full sampler + MDN scoring").
+"""Docking jobs on the device: batch assembly -> reverse-SDE sampler -> MDN rescoring -> one gather.
 
-The reference writes every sampled pose to PDB/SDF and re-parses it with ProDy/RDKit before ``Scorer`` runs
-(``DiffBindFR/app/predict.py:141-158``, ``scoring/dataset/pipeline.py:23-69``).  Here the sampler's atom14 output feeds
-the MDN featuriser (``mdn_features``, a restatement of ``protein_feature.py:170-217``) directly on the device; the
-pose-independent inputs (backbone dihedrals, ligand atom/bond features) come from the dataset featuriser once per complex.
+What ``DiffBindFR/app/predict.py`` does around the hot path, restated for the B200 path (BASELINE.json configs[2..4]):
+
+* the job is the list of (pair, pose) samples in the reference's pose-major order (``inference_dataset.py:480-490``:
+  sample i = pose ``i // n_pairs`` of pair ``i % n_pairs``), dealt round-robin to the ranks by ``shard.run_sharded``;
+* every rank uploads each COMPLEX of a batch once and replicates / randomises its poses on the device
+  (``Engine.expand``: ``collate.py:18-137`` + ``LigInit`` / ``SCProtInit`` of ``struct_init.py`` with a per-sample Philox stream);
+* all denoising steps of the batch run inside one C-ABI call (``Engine.sample_expanded``);
+* the MDN scorer (``common.engines.Scorer``, ``engines.py:230-302``) runs on the same rank straight from the sampler's
+  atom14 output - the reference writes every pose to PDB/SDF and re-parses it with ProDy/RDKit first
+  (``predict.py:141-158``, ``scoring/dataset/pipeline.py:23-69``) - with the knn-30 graph and the GVP features built by a CUDA
+  kernel (``MDNScorer.featurize``);
+* final coordinates and scores travel in ONE ``all_gather`` of fixed-stride records (``shard.gather_poses``).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
-from . import mdn_features
+from . import batch as batch_mod
+from . import mdn_features, shard, synth
+from .engine import Engine
+from .mdn import MDNScorer
 
 
-def mdn_inputs_from_poses(lig_pos: torch.Tensor, atom14: torch.Tensor, batch: Dict[str, object], static: Sequence[Dict[str, torch.Tensor]],
+def job_samples(complexes: Sequence[Dict[str, np.ndarray]], n_poses: int) -> List[Dict[str, object]]:
+    """The (pair, pose) sample list in the reference's pose-major order; light records that point at their complex."""
+    n = len(complexes)
+    return [dict(id=k * n + p, complex=p, pose=k, lig_pos=complexes[p]["lig_pos"], sequence=complexes[p]["sequence"])
+            for k in range(n_poses) for p in range(n)]
+
+
+class Docker:
+    """Sampler + MDN scorer of one device."""
+
+    def __init__(self, device: int, sd: Dict[str, torch.Tensor], mdn_sd: Optional[Dict[str, torch.Tensor]] = None, conv_kernel: int = 6):
+        self.eng = Engine(device, conv_kernel=conv_kernel)
+        self.eng.load_state_dict(sd)
+        self.scorer = None
+        if mdn_sd is not None:
+            self.scorer = MDNScorer(self.eng)
+            self.scorer.load_state_dict(mdn_sd)
+        self.device = torch.device("cuda", device)
+        self.stats = dict(batches=0, device_ms=0.0, h2d_bytes=0, d2h_bytes=0, launches=0)
+        self._ev: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+
+    # ------------------------------------------------------------------ one batch
+    def _mdn_inputs(self, complexes, comp_of_graph: Sequence[int], cb, lig: torch.Tensor, a14: torch.Tensor) -> Dict[str, torch.Tensor]:
+        dev = self.device
+        st = [complexes[c]["mdn"] for c in comp_of_graph]
+        amask = self.eng.view(cb, "atom14_mask")
+        res_ptr = self.eng.view(cb, "res_ptr")
+        bb = torch.from_numpy(np.concatenate([s["bb_dihedral_sincos"] for s in st])).to(dev)
+        x = self.scorer.featurize(a14, res_ptr, amask, bb)
+        x["pro_seq"] = torch.from_numpy(np.concatenate([s["seq"] for s in st])).to(dev)
+        nl = np.array([s["lig_node_s"].shape[0] for s in st])
+        off = np.concatenate([[0], np.cumsum(nl)])
+        x["lig_node_s"] = torch.from_numpy(np.concatenate([s["lig_node_s"] for s in st])).to(dev)
+        x["lig_edge_s"] = torch.from_numpy(np.concatenate([s["lig_edge_s"] for s in st])).to(dev)
+        x["lig_edge_index"] = torch.from_numpy(np.concatenate([s["lig_edge_index"] + off[i] for i, s in enumerate(st)], axis=1)).to(dev)
+        x["lig_cov_edge_mask"] = torch.ones(x["lig_edge_index"].shape[1], dtype=torch.bool, device=dev)
+        x["lig_pos"] = lig
+        x["lig_batch"] = self.eng.view(cb, "lig_batch").long()
+        return x
+
+    def dock_batch(self, complexes, samples: Sequence[Dict[str, object]], steps, seed: int = 0, tr_sigma_max: float = 10.0,
+                   noise_seed: int = 1) -> List[Tuple[torch.Tensor, torch.Tensor, float]]:
+        """``samples``: records of ``job_samples`` (any mix of complexes / poses).  Returns per sample
+        (ligand xyz (n_l,3), atom14 (n_r,14,3)[, MDN score]) on the host."""
+        comp = sorted({int(s["complex"]) for s in samples})
+        slot = {c: i for i, c in enumerate(comp)}
+        base = batch_mod.prepare(synth.collate([complexes[c] for c in comp]))
+        src = [slot[int(s["complex"])] for s in samples]
+        ids = [int(s["id"]) for s in samples]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cb = self.eng.expand(base, src, ids, seed=seed, tr_sigma_max=tr_sigma_max)
+        g = torch.Generator().manual_seed(noise_seed * 1000003 + ids[0])
+        noise = torch.randn(len(steps), 6 * cb.B + cb.n_tor + cb.n_sc, generator=g)
+        if len(steps):
+            noise[-1] = 0.0                                  # no_final_step_noise (diffbindfr_ts.py:144-163)
+        lig, a14 = self.eng.sample_expanded(cb, steps, noise)
+        launches = self.eng.launch_count()
+        scores = None
+        if self.scorer is not None:
+            comp_of_graph = [int(s["complex"]) for s in samples]
+            x = self._mdn_inputs(complexes, comp_of_graph, cb, lig, a14)
+            scores = self.scorer.forward(x)
+        e1.record()
+        self._ev.append((e0, e1))
+        lp = self.eng.view(cb, "lig_ptr").cpu().numpy(); rp = self.eng.view(cb, "res_ptr").cpu().numpy()
+        lig_h, a14_h = lig.cpu(), a14.cpu()
+        sc_h = scores.cpu().tolist() if scores is not None else None
+        self.stats["batches"] += 1
+        self.stats["launches"] += launches
+        self.stats["h2d_bytes"] += sum(int(v.nbytes) for k, v in base.items() if k != "dims") + noise.numel() * 4
+        self.stats["d2h_bytes"] += lig_h.numel() * 4 + a14_h.numel() * 4 + (len(samples) * 4 if sc_h is not None else 0)
+        out = []
+        for i in range(len(samples)):
+            r = (lig_h[lp[i]:lp[i + 1]], a14_h[rp[i]:rp[i + 1]])
+            out.append(r + (sc_h[i],) if sc_h is not None else r)
+        return out
+
+    def device_ms(self) -> float:
+        """Summed CUDA-event time of the batches run so far (first kernel of a batch to its last), then reset."""
+        torch.cuda.synchronize(self.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._ev)
+        self._ev = []
+        return ms
+
+    # ------------------------------------------------------------------ whole job, sharded over the ranks
+    def dock(self, complexes, n_poses: int, steps, batch_size: int = 320, seed: int = 0, tr_sigma_max: float = 10.0,
+             noise_seed: int = 1, group=None):
+        """All ``len(complexes) * n_poses`` samples; every rank returns {sample id: (lig, atom14[, score])} for the whole job."""
+        samples = job_samples(complexes, n_poses)
+        run = lambda chunk: self.dock_batch(complexes, chunk, steps, seed, tr_sigma_max, noise_seed)
+        nccl = torch.distributed.is_initialized() and torch.distributed.get_backend(group) == "nccl"
+        return shard.run_sharded(samples, run, batch_size, group=group, device=self.device if nccl else None)
+
+
+def mdn_inputs_from_poses_torch(lig_pos: torch.Tensor, atom14: torch.Tensor, batch: Dict[str, object], static: Sequence[Dict[str, torch.Tensor]],
                           poses_per_complex: int, topk: int = 30) -> Dict[str, torch.Tensor]:
-    """Collated MDN scorer inputs (flat dict, see ``synth.make_mdn_complexes``) for the B = n_complex * poses graphs of a
+    """(Cross-check path: torch ops of ``mdn_features`` instead of the CUDA featuriser.)  Collated MDN scorer inputs (flat dict, see ``synth.make_mdn_complexes``) for the B = n_complex * poses graphs of a
     sampler batch laid out pose-major per complex (``synth.make_batch``).  ``static[c]``: ``atom14_mask`` (n,14),
     ``bb_dihedral_sincos`` (n,6), ``seq`` (n,), ``lig_node_s`` (n_l,89), ``lig_edge_s`` (E,20), ``lig_edge_index`` (2,E) covalent."""
     dev = atom14.device
@@ -56,7 +164,24 @@ def mdn_inputs_from_poses(lig_pos: torch.Tensor, atom14: torch.Tensor, batch: Di
 
 
 def dock_and_score(engine, scorer, batch, steps, noise, static, poses_per_complex: int):
-    """One batch through the reverse-SDE sampler and the MDN scorer; returns (lig (N_l,3), atom14 (N_r,14,3), scores (B,)) on device."""
+    """One host-collated batch (``synth.make_batch`` layout: ``poses_per_complex`` consecutive graphs per complex) through the
+    sampler and the MDN scorer; returns (lig (N_l,3), atom14 (N_r,14,3), scores (B,)) on the device.  ``static[c]``:
+    ``synth.make_mdn_static``."""
     lig, a14, _, _ = engine.sample(batch, steps, noise)
-    x = mdn_inputs_from_poses(lig, a14, batch, static, poses_per_complex)
+    dev = a14.device
+    B = int(batch["num_graphs"])
+    amask = torch.as_tensor(batch["atom14_mask"]).to(torch.uint8).to(dev)
+    res_ptr = torch.as_tensor(batch["res_ptr"])
+    comp = [g // poses_per_complex for g in range(B)]
+    bb = torch.cat([static[c]["bb_dihedral_sincos"] for c in comp]).to(dev)
+    x = scorer.featurize(a14, res_ptr, amask, bb)
+    x["pro_seq"] = torch.cat([static[c]["seq"] for c in comp]).to(dev)
+    nl = [static[c]["lig_node_s"].shape[0] for c in comp]
+    off = np.concatenate([[0], np.cumsum(nl)])
+    x["lig_node_s"] = torch.cat([static[c]["lig_node_s"] for c in comp]).to(dev)
+    x["lig_edge_s"] = torch.cat([static[c]["lig_edge_s"] for c in comp]).to(dev)
+    x["lig_edge_index"] = torch.cat([static[c]["lig_edge_index"] + int(off[i]) for i, c in enumerate(comp)], 1).to(dev)
+    x["lig_cov_edge_mask"] = torch.ones(x["lig_edge_index"].shape[1], dtype=torch.bool, device=dev)
+    x["lig_pos"] = lig
+    x["lig_batch"] = torch.as_tensor(batch["lig_node_batch"]).to(dev)
     return lig, a14, scorer.forward(x)

@@ -371,3 +371,56 @@ def make_mdn_static(batch: Dict[str, object], poses_per_complex: int, seed: int 
                         lig_node_s=(torch.rand(nl, 89, generator=g) < 0.15).float(),
                         lig_edge_s=(torch.rand(cov.shape[1], 20, generator=g) < 0.25).float(), lig_edge_index=cov))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ docking jobs
+def attach_mdn_static(sample: Dict[str, np.ndarray], rng) -> Dict[str, np.ndarray]:
+    """Pose-independent MDN scorer inputs of one complex (what the dataset featuriser provides once per pair,
+    DiffBindFR/scoring/dataset/pipeline.py:23-69): backbone dihedral sin/cos (synthetic angles), ligand atom (89) / covalent bond
+    (20) features, covalent edge list (both directions).  Stored under ``sample['mdn']``; shared by every pose of the complex."""
+    n, nl = int(sample["sequence"].shape[0]), int(sample["lig_pos"].shape[0])
+    ang = rng.uniform(-math.pi, math.pi, size=(n, 3))
+    cov = np.asarray(sample["lig_edge_index"], dtype=np.int64)
+    sample["mdn"] = dict(
+        seq=np.asarray(sample["sequence"], dtype=np.int64),
+        bb_dihedral_sincos=np.stack([np.sin(ang), np.cos(ang)], -1).reshape(n, 6).astype(np.float32),
+        lig_node_s=(rng.random((nl, 89)) < 0.15).astype(np.float32),
+        lig_edge_s=(rng.random((cov.shape[1], 20)) < 0.25).astype(np.float32),
+        lig_edge_index=cov)
+    return sample
+
+
+def make_complexes(n_complex: int, n_res=36, n_lig=30, seed: int = 0, radius: float = 12.0, tr_sigma: float = 3.0,
+                   shared_ligand: bool = False, mdn: bool = True) -> List[Dict[str, np.ndarray]]:
+    """``n_complex`` (pocket, ligand) pairs, one sample each (the starting poses of a docking job are drawn on the device).
+    ``n_res`` / ``n_lig``: ints or (lo, hi) ranges (PoseBusters-shape sets); ``shared_ligand``: reverse docking, ONE ligand
+    against ``n_complex`` receptors (BASELINE.json configs[4])."""
+    rng = np.random.default_rng(seed)
+    out, lig0 = [], None
+    for _ in range(n_complex):
+        nr = int(rng.integers(n_res[0], n_res[1] + 1)) if isinstance(n_res, (tuple, list)) else int(n_res)
+        nl = int(rng.integers(n_lig[0], n_lig[1] + 1)) if isinstance(n_lig, (tuple, list)) else int(n_lig)
+        rad = radius * (nr / 36.0) ** (1.0 / 3.0)
+        s = make_pocket(rng, nr, rad)
+        if shared_ligand and lig0 is not None:
+            s.update({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in lig0.items()})
+        else:
+            lig = make_ligand(rng, nl, tr_sigma)
+            s.update(lig)
+            if shared_ligand:
+                lig0 = lig
+        if mdn:
+            attach_mdn_static(s, rng)
+        out.append(s)
+    return out
+
+
+JOBS = {
+    # BASELINE.json configs[0..4] as docking jobs: (complexes, poses per complex)
+    "3dbs": dict(n_complex=1, n_poses=1, n_res=105, n_lig=35),
+    "3dbs_x40": dict(n_complex=1, n_poses=40, n_res=105, n_lig=35),
+    "cfgA": dict(n_complex=1, n_poses=40, n_res=36, n_lig=30),
+    "cfg3_16x40": dict(n_complex=16, n_poses=40, n_res=36, n_lig=30),
+    "posebusters_256x40": dict(n_complex=256, n_poses=40, n_res=(30, 110), n_lig=(15, 50)),
+    "revdock_512x40": dict(n_complex=512, n_poses=40, n_res=36, n_lig=30, shared_ligand=True),
+}

@@ -214,6 +214,25 @@ int b200dock_sample(B200Handle* h, B200Batch* batch, const B200Step* steps, int 
                     const float* time_emb /* host [n_steps][32] */, const float* noise,
                     float* lig_traj, float* atom14_out, float* atom14_traj, void* stream);
 
+/* Batch assembly on the device.  `base` holds every COMPLEX once (host pointers, same struct as for
+ * b200dock_sample_host); output graph g is a copy of base graph src_graph[g] (index arrays shifted), optionally with a fresh
+ * starting pose: LigInit (druglib/datasets/Docking/struct_init.py:16-53: uniform torsions, uniformly random rotation,
+ * N(0, tr_sigma_max^2) translation) and SCProtInit (:113-136: chi ~ U(-pi, pi) on the existing chi angles, atom14 rebuilt),
+ * drawn from a Philox4x32-10 stream keyed by (seed, stream_id[g]) so that a sample's pose does not depend on the batch or
+ * rank it lands in.  Replaces the 40x host collation of the same pocket (druglib/data/collate.py:18-137).  `out` receives
+ * DEVICE pointers owned by the handle (valid until the next b200dock_expand_host / destroy); pass it to b200dock_sample.
+ * Asynchronous on `stream` after the staging memcpy. */
+typedef struct {
+  int32_t B_out;
+  int32_t randomize;              /* 0: plain replication; 1: LigInit + SCProtInit on the device */
+  const int32_t* src_graph;       /* host [B_out] */
+  const uint64_t* stream_id;      /* host [B_out] RNG stream of every output graph (e.g. global sample id) */
+  uint64_t seed;
+  float tr_sigma_max;             /* LigInit(tr_sigma_max), DiffBindFR/configs/diffbindfr_ts.py */
+  float reserved;
+} B200Expand;
+int b200dock_expand_host(B200Handle* h, const B200Batch* base_host, const B200Expand* ex, B200Batch* out_dev, void* stream);
+
 /* Deferred end-of-call check (see "Synchronisation" above). */
 int b200dock_set_deferred_check(B200Handle* h, int on);
 int b200dock_check(B200Handle* h, void* stream);
@@ -281,6 +300,28 @@ typedef struct {
 int b200dock_mdn_load_encoder_weights(B200Handle* h, const float* blob, size_t n, const int64_t* offsets, int n_offsets);
 /* pro_s: device [N_r][128]; lig_s: device [N_l][128]. Asynchronous on `stream`. */
 int b200dock_mdn_encode(B200Handle* h, const B200MdnGraph* g, float* pro_s, float* lig_s, void* stream);
+
+/* MDN protein featurisation from the sampler's atom14 output: replaces get_protein_feature's geometry part
+ * DiffBindFR/scoring/dataset/protein_feature.py:170-217 and its torch_cluster.knn_graph(CA, k=topk) call.  One graph per pose;
+ * edges are emitted grouped by centre (edge_index[1]) in ascending centre order, neighbours by ascending distance, so
+ * node_ptr is the CSR b200dock_mdn_encode needs (perm = identity).  All pointers are device pointers. */
+typedef struct {
+  int32_t B, N_r, topk, max_res;  /* max_res = largest graph (residues); topk <= 32 */
+  int64_t E;                      /* sum_g n_g * min(topk, n_g - 1) */
+  const int32_t* res_ptr;         /* [B+1] */
+  const int64_t* edge_ptr;        /* [B+1] prefix sum of n_g * min(topk, n_g - 1) */
+  const float* atom14;            /* [N_r][14][3] (missing atoms = 0) */
+  const uint8_t* atom14_mask;     /* [N_r][14] */
+  const float* bb_sincos;         /* [N_r][6] backbone dihedral sin/cos (pose independent) */
+  float* node_s;                  /* out [N_r][9] */
+  float* node_v;                  /* out [N_r][3][3] */
+  int32_t* edge_src;              /* out [E] edge_index[0] (neighbour) */
+  int32_t* edge_dst;              /* out [E] edge_index[1] (centre) */
+  float* edge_s;                  /* out [E][21] */
+  float* edge_v;                  /* out [E][1][3] */
+  int32_t* node_ptr;              /* out [N_r+1] */
+} B200MdnFeat;
+int b200dock_mdn_featurize(B200Handle* h, const B200MdnFeat* f, void* stream);
 
 /* Introspection for tests / benchmarks: edge counts of the last evaluation
  * [E_ll, E_aa, E_al(=E_la), E_tor, E_sc], kernels launched by the last call, device time of the

@@ -1,4 +1,5 @@
 """MDN scoring head: oracle vs the reference fixture (CPU) and the CUDA kernel vs both (GPU)."""
+import numpy as np
 import pytest
 import torch
 
@@ -171,10 +172,47 @@ def test_sampler_to_mdn_pipeline_matches_oracle_scorer():
     noise = torch.randn(4, 6 * B + n_tor + n_sc, generator=torch.Generator().manual_seed(2))
     lig, a14, scores = pipeline.dock_and_score(eng, sc, b, sch, noise, static, P)
     torch.cuda.synchronize()
-    x = pipeline.mdn_inputs_from_poses(lig.cpu(), a14.cpu(), b, static, P)
+    x = pipeline.mdn_inputs_from_poses_torch(lig.cpu(), a14.cpu(), b, static, P)
     ref = oenc.karmadock_forward(ksd, x)
     assert scores.shape == (B,) and torch.isfinite(scores).all()
     assert torch.allclose(scores.cpu(), ref, rtol=2e-4, atol=1e-4), (scores.cpu(), ref)
+
+
+@pytest.mark.gpu
+def test_cuda_featuriser_matches_torch_restatement():
+    """SURVEY 8(f) rank 2 as a kernel: ``b200dock_mdn_featurize`` (knn-30 over CA + node / edge features, one block per pose)
+    against ``mdn_features.protein_features`` - the restatement pinned to the reference's own ``get_protein_feature`` body
+    (``test_protein_featuriser_matches_reference_function_body``) - on a ragged batch incl. a pocket smaller than k: identical
+    edge lists (neighbour order by ascending distance), features within 2e-6, CSR = identity."""
+    from diffbindfr_b200.engine import Engine
+    from diffbindfr_b200.mdn import MDNScorer
+    from diffbindfr_b200 import mdn_features
+    rng = np.random.default_rng(3)
+    sizes = [36, 12, 70, 31]
+    a14s, masks, bbs = [], [], []
+    for n in sizes:
+        pk = synth.make_pocket(rng, n, 12.0 * max(n / 36.0, 1.0) ** (1.0 / 3.0))
+        a14s.append(torch.from_numpy(pk["atom14_position"]).float()); masks.append(torch.from_numpy(pk["atom14_mask"].astype(np.uint8)))
+        ang = torch.from_numpy(rng.uniform(-np.pi, np.pi, size=(n, 3))).float()
+        bbs.append(torch.stack([ang.sin(), ang.cos()], -1).reshape(n, 6))
+    sc = MDNScorer(Engine(0))
+    res_ptr = np.concatenate([[0], np.cumsum(sizes)])
+    x = sc.featurize(torch.cat(a14s).cuda(), res_ptr, torch.cat(masks), torch.cat(bbs))
+    torch.cuda.synchronize()
+    e_off = r_off = 0
+    for g, n in enumerate(sizes):
+        ref = mdn_features.protein_features(a14s[g], masks[g].float(), bbs[g], 30)
+        E = ref["edge_index"].shape[1]
+        ei = x["pro_edge_index"][:, e_off:e_off + E].cpu().long() - r_off
+        assert torch.equal(ei, ref["edge_index"]), g
+        assert torch.allclose(x["pro_node_s"][r_off:r_off + n].cpu(), ref["node_s"], atol=2e-6), g
+        assert torch.allclose(x["pro_node_v"][r_off:r_off + n].cpu(), ref["node_v"], atol=2e-6), g
+        assert torch.allclose(x["pro_edge_s"][e_off:e_off + E].cpu(), ref["edge_s"], atol=2e-6), g
+        assert torch.allclose(x["pro_edge_v"][e_off:e_off + E].cpu(), ref["edge_v"], atol=2e-6), g
+        ptr = x["pro_node_ptr"][r_off:r_off + n + 1].cpu()
+        assert torch.equal(ptr, e_off + torch.arange(n + 1, dtype=torch.int32) * min(30, n - 1)), g
+        e_off += E; r_off += n
+    assert x["pro_edge_index"].shape[1] == e_off
 
 
 @pytest.mark.parametrize("tag", ["n36", "n20_small_k", "n105"])

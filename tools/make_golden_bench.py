@@ -4,7 +4,8 @@
 reference fixtures, tools/make_golden.py).  bench.py compares the coordinates of its timed run with this file and prints
 the distance under ``parity``; tests/test_gpu_parity.py asserts the 1e-3 A bar on it.
 
-    python tools/make_golden_bench.py [--workload cfgA] [--steps 20] [--threads 8]     # ~5-10 min of CPU
+    python tools/make_golden_bench.py [--workload cfgA] [--steps 20] [--threads 8]     # ~12 min of CPU
+    python tools/make_golden_bench.py --workload 3dbs_x40 --poses 2                    # configs[0] shape, first two poses
 
 Output: tests/golden/bench_<workload>_s<steps>.pt  (final ligand xyz, final atom14, ligand xyz after every step)
 """
@@ -47,15 +48,27 @@ def main():
     ap.add_argument("--noise-seed", type=int, default=1)
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--dtype", default="float32")
+    ap.add_argument("--poses", type=int, default=0, help="only the first POSES poses of the workload (a batch is a disjoint union of "
+                    "poses and the kernels are batch-composition independent, so they check the same poses inside the full batch)")
     args = ap.parse_args()
     torch.set_num_threads(args.threads)
-    b = synth.make_batch(**synth.WORKLOADS[args.workload], seed=args.seed)
+    kw = dict(synth.WORKLOADS[args.workload])
+    if args.poses:
+        kw["n_poses"] = args.poses
+    b = synth.make_batch(**kw, seed=args.seed)
     sd = weights.random_state_dict(0)
     B, n_tor, n_sc = b["num_graphs"], int(b["tor_edge_mask"].sum()), int(b["sc_torsion_edge_mask"].sum())
     n = args.steps
     sch = schedule.make_schedule()
     sch = [sch[i % len(sch)] for i in range(n)]
-    noise = unpack_noise(bench_noise(b, n, args.noise_seed), B, n_tor, n_sc)
+    if args.poses:   # noise of the FULL workload batch (what bench.py draws), cut down to the first poses (graph-major layouts: prefixes)
+        bf = synth.make_batch(**synth.WORKLOADS[args.workload], seed=args.seed)
+        Bf, tf, sf = bf["num_graphs"], int(bf["tor_edge_mask"].sum()), int(bf["sc_torsion_edge_mask"].sum())
+        assert torch.equal(torch.as_tensor(bf["lig_pos"])[:b["lig_pos"].shape[0]], torch.as_tensor(b["lig_pos"]))
+        full = unpack_noise(bench_noise(bf, n, args.noise_seed), Bf, tf, sf)
+        noise = [dict(tr=z["tr"][:B], rot=z["rot"][:B], tor=z["tor"][:n_tor], sc=z["sc"][:n_sc]) for z in full]
+    else:
+        noise = unpack_noise(bench_noise(b, n, args.noise_seed), B, n_tor, n_sc)
     cfg = dict(osampler.CFG); cfg["actual_steps"] = n
     trace = []
     t0 = time.perf_counter()
@@ -63,7 +76,7 @@ def main():
                                rot_norm_fn=lambda x: min(sch, key=lambda s: abs(s.rot_sigma - x)).rot_score_norm,
                                tor_norm_fn=lambda x: min(sch, key=lambda s: abs(s.sc_tor_sigma - x)).tor_score_norm2)
     dt = time.perf_counter() - t0
-    out = dict(workload=args.workload, seed=args.seed, noise_seed=args.noise_seed, steps=n, dtype=args.dtype,
+    out = dict(workload=args.workload, poses=int(b["num_graphs"]), seed=args.seed, noise_seed=args.noise_seed, steps=n, dtype=args.dtype,
                batch_checksum=batch_checksum(b), lig_final=lig.float(), atom14_final=a14.float(),
                lig_traj=torch.stack([t["lig_pos"].float() for t in trace]), oracle="O2 oracle/sampler.py",
                cpu_seconds=dt, threads=args.threads)

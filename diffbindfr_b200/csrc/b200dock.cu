@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges are emitted only when B200DOCK_NVTX=1 (nsys / ncu --nvtx)
+
 #include "common.cuh"
 #include "graph.cuh"
 #include "embed.cuh"
@@ -89,6 +91,7 @@ struct B200Handle {
   int tp_grid = 148;
   std::vector<float> cg_dense; int atom14_group[21 * 14];
   // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
+  bool nvtx = false;
   int* host_meta = nullptr; bool deferred_check = false; size_t feat_smem = 48 * 1024;
   Buf ex_in, ex_pin, ex_out[32];   // batch assembly: staged base batch (device / pinned) and the expanded arrays
   Buf trace; bool trace_on = false;
@@ -96,6 +99,12 @@ struct B200Handle {
 };
 
 namespace {
+
+struct NvtxRange {               // RAII range on the calling thread: marks the phases of one evaluation in a timeline
+  bool on;
+  NvtxRange(const B200Handle* h, const char* name) : on(h->nvtx) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 int ensure(B200Handle* h, Buf& b, size_t bytes) {
   if (bytes <= b.cap) return B200_OK;
@@ -296,6 +305,7 @@ static inline void side_join(B200Handle* h, cudaStream_t st) {
 int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr, float* rot, float* tor, float* sc,
                  cudaStream_t st) {
   if (!h->weights) FAIL(B200_ERR_STATE, "weights not loaded");
+  NvtxRange r_score(h, "b200dock.score_network");
   const float* W = h->d_blob;
   const std::vector<int64_t>& off = h->off;
   // ---- sigma pre-activations
@@ -347,6 +357,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
   // ---- six interaction layers
   float* hl = h->h_lig.as<float>(); float* ha = h->h_atom.as<float>();
   for (int l = 0; l < h->debug_layers; ++l) {
+    NvtxRange r_layer(h, "b200dock.interaction_layer");
     const int plan = plan_of_layer(l);
     ConvLaunch L{};
     Fused16Extra X{};
@@ -370,6 +381,7 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     side_join(h, st);
     h->launches += 2;
   }
+  NvtxRange r_heads(h, "b200dock.heads");
   // ---- translation / rotation heads (side stream: independent of the pseudo-torque convs below)
   cudaStream_t s3 = side_fork(h, st);
   {
@@ -469,6 +481,7 @@ int sample_device(B200Handle* h, B200Batch& b, const B200Step* steps, int n_step
   const size_t nstride = (size_t)6 * b.B + b.n_tor + b.n_sc;
   const int maxn = std::max(std::max(b.B * SIG, b.n_tor), b.n_sc);
   for (int s = 0; s < n_steps; ++s) {
+    NvtxRange r_step(h, "b200dock.denoising_step");
     k_fill_cond<<<cdiv(maxn, 256), 256, 0, st>>>(b.B, b.n_tor, b.n_sc, h->temb_steps.as<float>() + (size_t)s * SIG, steps[s],
                                                  h->c_temb.as<float>(), h->c_trs.as<float>(), h->c_rotn.as<float>(),
                                                  h->c_torn.as<float>(), h->c_scn.as<float>());
@@ -524,6 +537,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   h->n_sms = prop.multiProcessorCount;
   h->tp_grid = h->n_sms;
   if (const char* g = getenv("B200DOCK_NO_SIDE")) h->use_side = atoi(g) == 0;
+  if (const char* g = getenv("B200DOCK_NVTX")) h->nvtx = atoi(g) != 0;
   CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));

@@ -246,6 +246,12 @@ k_conv_v3(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
       const uint32_t mine = (warp == 1) ? 0u : 1u;
       tc::Phase st;
       uint32_t useq = 0;
+      uint64_t dhs[NST], dls[NST];                     // shared-memory descriptors of the ring stages (loop invariant)
+#pragma unroll
+      for (int i = 0; i < NST; ++i) {
+        const uint32_t b_hi = tc::smem_u32(sB + (size_t)i * 2 * B_PART);
+        dhs[i] = tc::make_desc(b_hi); dls[i] = tc::make_desc(b_hi + B_PART);
+      }
       auto issue = [&](int N, uint32_t abase, uint64_t* full_bar, bool last_of_tile, uint32_t abuf) {
         const uint32_t db = useq & 1, dpar = (useq >> 1) & 1;
         ++useq;
@@ -255,15 +261,17 @@ k_conv_v3(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(V3_D0 + db * V3_DW);
         const uint32_t idesc = tc::make_idesc_f16(256, N);
-        tc::mbar_wait_cluster(&d_empty[db], dpar ^ 1);
-        tc::fence_after();
 #pragma unroll
         for (int ka = 0; ka < KATOMS; ++ka) {
           tc::mbar_wait_cluster(&b_full[st.idx], st.par);
+          const uint64_t dh = dhs[st.idx], dl = dls[st.idx];
+          if (ka == 0) {
+            // the accumulator hand-shake sits on the critical path (a 96-column unit is only 1392 tensor cycles): everything that
+            // does not need the accumulator - weights landed, descriptors ready - is done BEFORE waiting for the fold warps
+            tc::mbar_wait_cluster(&d_empty[db], dpar ^ 1);
+          }
           tc::fence_after();
           if (tc::elect_one()) {
-            const uint32_t b_hi = tc::smem_u32(sB + (size_t)st.idx * 2 * B_PART);
-            const uint64_t dh = tc::make_desc(b_hi), dl = tc::make_desc(b_hi + B_PART);
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
               if (ka == KATOMS - 1 && k8 >= 2) continue;     // K = 145 real columns: halves 160..191 are zero padding

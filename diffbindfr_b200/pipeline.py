@@ -68,9 +68,9 @@ class Docker:
         return x
 
     def dock_batch(self, complexes, samples: Sequence[Dict[str, object]], steps, seed: int = 0, tr_sigma_max: float = 10.0,
-                   noise_seed: int = 1) -> List[Tuple[torch.Tensor, torch.Tensor, float]]:
-        """``samples``: records of ``job_samples`` (any mix of complexes / poses).  Returns per sample
-        (ligand xyz (n_l,3), atom14 (n_r,14,3)[, MDN score]) on the host."""
+                   noise_seed: int = 1) -> "shard.BatchResult":
+        """``samples``: records of ``job_samples`` (any mix of complexes / poses).  Returns the batch's final ligand coordinates,
+        atom14 coordinates and MDN scores as device tensors (``shard.BatchResult``)."""
         comp = sorted({int(s["complex"]) for s in samples})
         slot = {c: i for i, c in enumerate(comp)}
         base = batch_mod.prepare(synth.collate([complexes[c] for c in comp]))
@@ -92,18 +92,12 @@ class Docker:
             scores = self.scorer.forward(x)
         e1.record()
         self._ev.append((e0, e1))
-        lp = self.eng.view(cb, "lig_ptr").cpu().numpy(); rp = self.eng.view(cb, "res_ptr").cpu().numpy()
-        lig_h, a14_h = lig.cpu(), a14.cpu()
-        sc_h = scores.cpu().tolist() if scores is not None else None
         self.stats["batches"] += 1
         self.stats["launches"] += launches
         self.stats["h2d_bytes"] += sum(int(v.nbytes) for k, v in base.items() if k != "dims") + noise.numel() * 4
-        self.stats["d2h_bytes"] += lig_h.numel() * 4 + a14_h.numel() * 4 + (len(samples) * 4 if sc_h is not None else 0)
-        out = []
-        for i in range(len(samples)):
-            r = (lig_h[lp[i]:lp[i + 1]], a14_h[rp[i]:rp[i + 1]])
-            out.append(r + (sc_h[i],) if sc_h is not None else r)
-        return out
+        self.stats["d2h_bytes"] += (cb.N_l * 3 + cb.N_r * 42 + (len(samples) if scores is not None else 0)) * 4
+        # still batched: shard.run_sharded packs the records on the device (the library buffers are reused by the next batch)
+        return shard.BatchResult(lig, self.eng.view(cb, "lig_ptr"), a14, self.eng.view(cb, "res_ptr"), scores)
 
     def device_ms(self) -> float:
         """Summed CUDA-event time of the batches run so far (first kernel of a batch to its last), then reset."""
@@ -114,12 +108,12 @@ class Docker:
 
     # ------------------------------------------------------------------ whole job, sharded over the ranks
     def dock(self, complexes, n_poses: int, steps, batch_size: int = 320, seed: int = 0, tr_sigma_max: float = 10.0,
-             noise_seed: int = 1, group=None):
-        """All ``len(complexes) * n_poses`` samples; every rank returns {sample id: (lig, atom14[, score])} for the whole job."""
+             noise_seed: int = 1, group=None, unpack: bool = True):
+        """All ``len(complexes) * n_poses`` samples; every rank ends with {sample id: (lig, atom14[, score])} for the whole job
+        (``unpack=False``: the gathered record tensor and ``max_nl``, see ``shard.run_sharded``)."""
         samples = job_samples(complexes, n_poses)
         run = lambda chunk: self.dock_batch(complexes, chunk, steps, seed, tr_sigma_max, noise_seed)
-        nccl = torch.distributed.is_initialized() and torch.distributed.get_backend(group) == "nccl"
-        return shard.run_sharded(samples, run, batch_size, group=group, device=self.device if nccl else None)
+        return shard.run_sharded(samples, run, batch_size, group=group, device=self.device, unpack=unpack)
 
 
 def mdn_inputs_from_poses_torch(lig_pos: torch.Tensor, atom14: torch.Tensor, batch: Dict[str, object], static: Sequence[Dict[str, torch.Tensor]],

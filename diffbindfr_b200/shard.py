@@ -9,7 +9,7 @@ Works with NCCL (GPU tensors) and gloo (CPU tensors, used by the CPU tests).
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -40,6 +40,35 @@ def pack_records(ids: Sequence[int], ligs: Sequence[torch.Tensor], a14s: Sequenc
         rec[k, HDR:HDR + l.numel()] = l.reshape(-1).to(rec)
         rec[k, HDR + max_nl * 3:HDR + max_nl * 3 + a.numel()] = a.reshape(-1).to(rec)
     return rec
+
+
+class BatchResult(NamedTuple):
+    """Result of one device batch, still batched: what ``run_batch`` may return instead of per-sample tuples so that the records
+    are packed by a handful of tensor ops on the device (no per-sample Python, no per-sample D2H copy)."""
+    lig: torch.Tensor                 # (N_l, 3)
+    lig_ptr: torch.Tensor             # (B + 1,) int
+    atom14: torch.Tensor              # (N_r, 14, 3)
+    res_ptr: torch.Tensor             # (B + 1,) int
+    scores: Optional[torch.Tensor]    # (B,) or None
+
+
+def pack_batch(rec: torch.Tensor, slot0: int, ids: Sequence[int], br: BatchResult, max_nl: int) -> None:
+    """Vectorised ``pack_records`` of one batch into rows ``slot0 ...`` of the record tensor (same layout)."""
+    dev = rec.device
+    B = len(ids)
+    lp, rp = br.lig_ptr.to(dev).long(), br.res_ptr.to(dev).long()
+    nl, nr = lp[1:] - lp[:-1], rp[1:] - rp[:-1]
+    lig, a14 = br.lig.to(dev, torch.float32), br.atom14.to(dev, torch.float32).reshape(-1, 42)
+    rows = torch.repeat_interleave(torch.arange(B, device=dev), nl)
+    col = (torch.arange(lig.shape[0], device=dev) - lp[:-1][rows]) * 3 + HDR
+    rec[(slot0 + rows)[:, None], col[:, None] + torch.arange(3, device=dev)] = lig
+    rows = torch.repeat_interleave(torch.arange(B, device=dev), nr)
+    col = (torch.arange(a14.shape[0], device=dev) - rp[:-1][rows]) * 42 + HDR + max_nl * 3
+    rec[(slot0 + rows)[:, None], col[:, None] + torch.arange(42, device=dev)] = a14
+    rec[slot0:slot0 + B, 0] = torch.as_tensor(list(ids), dtype=torch.float32, device=dev)
+    rec[slot0:slot0 + B, 1] = nl.float(); rec[slot0:slot0 + B, 2] = nr.float()
+    if br.scores is not None:
+        rec[slot0:slot0 + B, 3] = br.scores.to(dev, torch.float32)
 
 
 def unpack_records(rec: torch.Tensor, max_nl: int, with_scores: Optional[bool] = None):
@@ -73,28 +102,54 @@ def gather_poses(ids, ligs, a14s, n_samples: int, max_nl: int, max_nr: int, grou
     return unpack_records(torch.stack(out).cpu(), max_nl)
 
 
-def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], List[Tuple[torch.Tensor, torch.Tensor]]],
-                batch_size: int, collate=None, group=None, device=None):
+def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], object], batch_size: int, collate=None, group=None, device=None,
+                unpack: bool = True):
     """Deal ``samples`` to ranks, run ``run_batch`` on local batches, gather all final poses.
-    ``run_batch(list_of_samples)`` returns [(lig (n_l,3), atom14 (n_r,14,3))] per sample, or 3-tuples with the sample's
-    MDN score appended (the scorer runs on the rank that sampled the pose; the score travels in the same record)."""
+    ``run_batch(list_of_samples)`` returns either [(lig (n_l,3), atom14 (n_r,14,3))] per sample - 3-tuples with the sample's MDN
+    score appended when the scorer ran on the rank that sampled the pose (the score travels in the same record) - or one
+    ``BatchResult`` for the whole batch (packed on the device without per-sample Python).  A sample record needs ``lig_pos`` and
+    ``sequence`` (sizes) and, optionally, ``id`` (default: its index).  ``unpack=False`` returns the gathered record tensor
+    ``(world, n_slots, stride)`` and ``max_nl`` instead of the per-sample dict (``unpack_records`` turns it into one later)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    mine = shard_indices(len(samples), rank, world)
+    n = len(samples)
+    mine = shard_indices(n, rank, world)
+    max_nl = max(int(s["lig_pos"].shape[0]) for s in samples)
+    max_nr = max(int(s["sequence"].shape[0]) for s in samples)
+    n_slots = (n + world - 1) // world
+    rec = None
     ids, ligs, a14s, scores = [], [], [], []
+    slot = 0
     for chunk in batches(mine, batch_size):
         res = run_batch([samples[i] for i in chunk])
+        cid = [int(samples[i].get("id", i)) if isinstance(samples[i], dict) else i for i in chunk]
+        if isinstance(res, BatchResult):
+            if rec is None:
+                rec = torch.zeros(n_slots, HDR + max_nl * 3 + max_nr * 42, dtype=torch.float32, device=device if device is not None else res.lig.device)
+                rec[:, 0] = -1
+                rec[:, 3] = float("nan")
+            pack_batch(rec, slot, cid, res, max_nl)
+            slot += len(chunk)
+            continue
         if len(res) != len(chunk):
             raise RuntimeError(f"run_batch returned {len(res)} results for {len(chunk)} samples")
-        for i, r in zip(chunk, res):
+        for i, r in zip(cid, res):
             ids.append(i); ligs.append(r[0]); a14s.append(r[1])
             if len(r) > 2:
                 scores.append(float(r[2]))
     if scores and len(scores) != len(ids):
         raise RuntimeError("run_batch returned a mix of scored and unscored samples")
-    max_nl = max(int(s["lig_pos"].shape[0]) for s in samples)
-    max_nr = max(int(s["sequence"].shape[0]) for s in samples)
-    return gather_poses(ids, ligs, a14s, len(samples), max_nl, max_nr, group, device, scores if scores else None)
+    if rec is None:
+        rec = pack_records(ids, ligs, a14s, max_nl, max_nr, n_slots, device, scores if scores else None)
+    elif ids:
+        raise RuntimeError("run_batch mixed BatchResult and per-sample results")
+    if world > 1:
+        out = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(out, rec, group=group)
+        rec = torch.stack(out)
+    if not unpack:
+        return rec, max_nl
+    return unpack_records(rec.cpu(), max_nl)
 
 
 def slice_noise(noise: Sequence[Dict[str, torch.Tensor]], graphs: Sequence[int], tor_per_graph: Sequence[int],

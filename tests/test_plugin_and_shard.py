@@ -291,3 +291,26 @@ def test_regroup_results_matches_reference_slicing():
             assert tuple(pn[p]) == got[p][0] and got[p][1].shape == (num_poses, 1, nl[p], 3) and got[p][2].shape == (num_poses, 1, nr[p], 14, 3)
             for k in range(num_poses):
                 assert torch.equal(got[p][1][k], results[p][k][0]) and torch.equal(got[p][2][k], results[p][k][1])
+
+
+def test_batch_result_packing_equals_per_sample_packing():
+    """``shard.pack_batch`` (vectorised, what the device path uses) writes the same record bytes as ``pack_records``."""
+    rng = np.random.default_rng(3)
+    samples = [synth.make_sample(rng, 5 + i, 7 + 2 * i) for i in range(4)]
+    ligs = [torch.from_numpy(s["lig_pos"]) + i for i, s in enumerate(samples)]
+    a14s = [torch.from_numpy(s["atom14_position"]) - i for i, s in enumerate(samples)]
+    max_nl, max_nr = max(l.shape[0] for l in ligs), max(a.shape[0] for a in a14s)
+    ids, sc = [11, 3, 7, 5], [0.5, -1.0, 2.0, 4.0]
+    want = shard.pack_records(ids, ligs, a14s, max_nl, max_nr, 6, None, sc)
+    rec = torch.zeros_like(want); rec[:, 0] = -1; rec[:, 3] = float("nan")
+    lp = torch.tensor([0] + list(np.cumsum([l.shape[0] for l in ligs])))
+    rp = torch.tensor([0] + list(np.cumsum([a.shape[0] for a in a14s])))
+    shard.pack_batch(rec, 0, ids[:2], shard.BatchResult(torch.cat(ligs[:2]), lp[:3], torch.cat(a14s[:2]), rp[:3], torch.tensor(sc[:2])), max_nl)
+    shard.pack_batch(rec, 2, ids[2:], shard.BatchResult(torch.cat(ligs[2:]), lp[2:] - lp[2], torch.cat(a14s[2:]), rp[2:] - rp[2], torch.tensor(sc[2:])), max_nl)
+    assert torch.equal(torch.nan_to_num(rec, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    got = shard.run_sharded([dict(s, id=i) for s, i in zip(samples, ids)],
+                            lambda ch: shard.BatchResult(torch.cat([torch.from_numpy(c["lig_pos"]) for c in ch]),
+                                                         torch.tensor([0] + list(np.cumsum([c["lig_pos"].shape[0] for c in ch]))),
+                                                         torch.cat([torch.from_numpy(c["atom14_position"]) for c in ch]),
+                                                         torch.tensor([0] + list(np.cumsum([c["sequence"].shape[0] for c in ch]))), None), 3)
+    assert sorted(got) == sorted(ids) and torch.allclose(got[7][0], torch.from_numpy(samples[2]["lig_pos"]))

@@ -227,6 +227,25 @@ def load_fixture(workload, K):
     return g if g["steps"] == K else None
 
 
+def cached_complexes(workload, kw):
+    """The synthetic complexes of a multi-complex job (seed 0).  Generating the 256 ragged PoseBusters-shape pockets takes about a
+    minute of host time per rank (self-avoiding CA walks), so the list is cached under .synth_cache/ (git-ignored; same bytes as a
+    fresh ``synth.make_complexes(seed=0, **kw)``); a missing cache file is simply regenerated."""
+    import pickle
+    path = os.path.join(ROOT, ".synth_cache", f"{workload}_{kw['n_complex']}.pkl")
+    if os.path.exists(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
+    cx = synth.make_complexes(seed=0, **kw)
+    if int(os.environ.get("RANK", "0")) == 0:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + f".{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:
+            pickle.dump(cx, f, protocol=4)
+        os.replace(tmp, path)
+    return cx
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -404,7 +423,7 @@ def main():
         P = kw.pop("n_poses")
         if args.complexes:
             kw["n_complex"] = args.complexes
-        complexes = synth.make_complexes(seed=0, **kw)
+        complexes = cached_complexes(args.workload, kw)
         n_samples = len(complexes) * P
         ksd = None if args.no_mdn else weights.random_karmadock_state_dict(0)
         dk = pipeline.Docker(local, sd, ksd, conv_kernel=args.conv_kernel)

@@ -24,6 +24,7 @@
 #include "mdn_enc.cuh"
 #include "mdn_feat.cuh"
 #include "assemble.cuh"
+#include "vina.cuh"
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -92,7 +93,7 @@ struct B200Handle {
   std::vector<float> cg_dense; int atom14_group[21 * 14];
   // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
   bool nvtx = false;
-  int* host_meta = nullptr; bool deferred_check = false; size_t feat_smem = 48 * 1024;
+  int* host_meta = nullptr; bool deferred_check = false; size_t feat_smem = 48 * 1024, vina_smem = 48 * 1024;
   Buf ex_in, ex_pin, ex_out[32];   // batch assembly: staged base batch (device / pinned) and the expanded arrays
   Buf trace; bool trace_on = false;
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool use_side = true;
@@ -225,7 +226,11 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const Fused16Extra& F, cudaStr
   int rc = B200_OK;
   const int k = h->cfg.conv_kernel;
   if (k == 10) rc = launch_conv_v3(L, F, h->tp_grid, st);
-  else if (k == 6) rc = launch_conv_fused16x2(L, F, h->tp_grid, st);
+  else if (k == 6) {
+    static const int dbg = getenv("B200DOCK_DBG") ? atoi(getenv("B200DOCK_DBG")) : 0;   // honoured by the -DB200DOCK_TRACE build only
+    ConvLaunch L2 = L; L2.dbg = dbg;
+    rc = launch_conv_fused16x2(L2, F, h->tp_grid, st);
+  }
   else if (k == 5) rc = launch_conv_fused16(L, F, h->tp_grid, st);
   else {
     k_conv_prologue<<<h->n_sms, PRO_THREADS, PRO_SMEM, st>>>(L);
@@ -962,6 +967,33 @@ int b200dock_mdn_featurize(B200Handle* h, const B200MdnFeat* f, void* stream) {
   A.node_s = f->node_s; A.node_v = f->node_v; A.edge_src = f->edge_src; A.edge_dst = f->edge_dst;
   A.edge_s = f->edge_s; A.edge_v = f->edge_v; A.node_ptr = f->node_ptr;
   k_mdn_featurize<<<f->B, 256, smem, (cudaStream_t)stream>>>(A);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200dock_vina(B200Handle* h, const B200Vina* v, void* stream) {
+  if (!h || !v) return B200_ERR_INVALID;
+  if (v->n_pose <= 0 || v->n_lig <= 0 || v->n_lig > VINA_MAX_LIG || v->n_tors < 0 || v->n_tors > VINA_MAX_TORS || v->n_rec <= 0 ||
+      v->n_rec > 10000 || v->root < 0 || v->root >= v->n_lig)
+    FAIL(B200_ERR_INVALID, "bad sizes for the error-correction stage (n_lig <= 128, n_tors <= 58, n_rec <= 10000)");
+  if (!v->lig_xyz || !v->lig_radius || !v->lig_flags || !v->rec_xyz || !v->rec_radius || !v->rec_flags || !v->pair_ptr || !v->out_energy ||
+      (v->n_tors && (!v->tors_axis || !v->tors_mask)) || (v->mode == 1 && !v->out_xyz))
+    FAIL(B200_ERR_INVALID, "null pointer in B200Vina");
+  CK(cudaSetDevice(h->device));
+  const size_t smem = vina_smem_bytes(v->n_rec);
+  if (smem > h->vina_smem) {
+    CK(cudaFuncSetAttribute(k_vina, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->vina_smem = smem;
+  }
+  VinaArgs A{};
+  A.n_pose = v->n_pose; A.n_lig = v->n_lig; A.n_rec = v->n_rec; A.n_tors = v->n_tors; A.root = v->root; A.max_steps = v->max_steps;
+  A.mode = v->mode; A.rec_pose_stride = v->rec_pose_stride;
+  A.lig_xyz = v->lig_xyz; A.lig_R = v->lig_radius; A.lig_flags = v->lig_flags;
+  A.rec_xyz = v->rec_xyz; A.rec_R = v->rec_radius; A.rec_flags = v->rec_flags;
+  A.tors_axis = v->tors_axis; A.tors_mask = v->tors_mask; A.pair_ptr = v->pair_ptr; A.pair_idx = v->pair_idx; A.n_rot = v->n_rot;
+  A.out_xyz = v->out_xyz; A.out_energy = v->out_energy; A.out_terms = v->out_terms; A.out_stats = v->out_stats;
+  k_vina<<<v->n_pose, VINA_THREADS, smem, (cudaStream_t)stream>>>(A);
   h->launches += 1;
   CK(cudaGetLastError());
   return B200_OK;

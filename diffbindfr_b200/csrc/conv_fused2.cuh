@@ -234,6 +234,11 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     float* xrow = x1s + row * F_X1S;
     float* scr = scat + q * 32 * SCAT_STRIDE;
+#ifdef B200DOCK_TRACE
+    const int dbg = L.dbg;            // timing experiments (B200DOCK_DBG): 1 no scatter, 2 no fold arithmetic, 4 no xin loads, 8 no H1 max pass, 16 no x1 gather
+#else
+    constexpr int dbg = 0;
+#endif
     const uint32_t x_full0 = tc::map_to_cta(x_full, 0), h_full0 = tc::map_to_cta(h_full, 0);
     const uint32_t d_empty0[2] = {tc::map_to_cta(&d_empty[0], 0), tc::map_to_cta(&d_empty[1], 0)};
     tc::Phase db;
@@ -287,12 +292,12 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           }
           float4 xf[36];                                 // the whole edge-input row in flight at once
 #pragma unroll
-          for (int k4 = 0; k4 < 12; ++k4) xf[k4] = __ldg(pe + k4);
+          for (int k4 = 0; k4 < 12; ++k4) xf[k4] = (dbg & 4) ? make_float4(0.1f, 0.2f, 0.3f, 0.4f) : __ldg(pe + k4);
 #pragma unroll
-          for (int k4 = 0; k4 < 12; ++k4) xf[12 + k4] = __ldg(pa + k4);
+          for (int k4 = 0; k4 < 12; ++k4) xf[12 + k4] = (dbg & 4) ? make_float4(0.1f, 0.2f, 0.3f, 0.4f) : __ldg(pa + k4);
 #pragma unroll
-          for (int k4 = 0; k4 < 12; ++k4) xf[24 + k4] = __ldg(pb0 + k4);
-          if (C.mode != 0) {
+          for (int k4 = 0; k4 < 12; ++k4) xf[24 + k4] = (dbg & 4) ? make_float4(0.1f, 0.2f, 0.3f, 0.4f) : __ldg(pb0 + k4);
+          if (C.mode != 0 && !(dbg & 4)) {
 #pragma unroll
             for (int k4 = 0; k4 < 12; ++k4) {
               float4 f2 = __ldg(pb1 + k4);
@@ -336,7 +341,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
               o[0] = f[j].x; o[1] = f[j].y; o[2] = f[j].z; o[3] = f[j].w;
             }
         };
-        x1_batch(0);
+        if (!(dbg & 16)) x1_batch(0);
         float shv[9];
 #pragma unroll
         for (int j = 0; j < 9; ++j) shv[j] = (j < C.sh_stride) ? C.sh[(size_t)e * C.sh_stride + j] : 0.0f;
@@ -351,7 +356,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           const float inv1 = C.inv_s1 / sx;              // D1 = (sx xin)(s1 W1)^T
           float mx = 1.0f;
 #pragma unroll 1
-          for (int g = 0; g < 9; ++g) {                  // pass 1: row maximum of relu(D1)
+          for (int g = 0; g < ((dbg & 8) ? 0 : 9); ++g) {                  // pass 1: row maximum of relu(D1)
             float v[16];
             tc::tmem_ld16(t0 + g * 16, v);
             tc::tmem_wait_ld();
@@ -383,7 +388,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           TRE_END(4);
         }
 #pragma unroll 1
-        for (int q0 = 14; q0 < nq; q0 += 14) x1_batch(q0);
+        for (int q0 = 14; q0 < ((dbg & 16) ? 0 : nq); q0 += 14) x1_batch(q0);
         // ---- 5. W2 units: fold with Z computed on the fly
         float o[48];
 #pragma unroll
@@ -420,14 +425,15 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           tc::fence_after();
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
-          if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);        // every unit is 144 columns wide (packer.py asserts it)
+          if (dbg & 2) { }
+          else if (pa.Wd == 48) tc::fold_unit_w48(taddr, xp, d1, M, zs, o);   // every unit is 144 columns wide (packer.py asserts it)
           else tc::fold_unit_w12(taddr, xp, d1, M, zs, o);                     // accumulators component-major, see the store below
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(d_empty0[db.idx]);
           tc::advance(db, 2);
           bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
-          if (last) {                                    // message block complete: segmented sum over the warp's 32 edges
+          if (last && !(dbg & 1)) {                      // message block complete: segmented sum over the warp's 32 edges
             float* my = scr + lane * SCAT_STRIDE;
             if (pa.Wd == 48) {
 #pragma unroll

@@ -26,7 +26,7 @@ EXPORTS = ["b200dock_create", "b200dock_destroy", "b200dock_last_error", "b200do
            "b200dock_last_edge_counts", "b200dock_last_launch_count", "b200dock_set_profiling",
            "b200dock_tp_kernel_time_ms", "b200dock_debug_tap", "b200dock_debug_set",
            "b200dock_mdn_load_weights", "b200dock_mdn_score",
-           "b200dock_mdn_load_encoder_weights", "b200dock_mdn_encode", "b200dock_mdn_featurize"]
+           "b200dock_mdn_load_encoder_weights", "b200dock_mdn_encode", "b200dock_mdn_featurize", "b200dock_vina"]
 
 
 class CCond(C.Structure):
@@ -83,6 +83,7 @@ def load_library(path: Optional[str] = None):
     lib.b200dock_mdn_load_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.b200dock_mdn_score.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
     lib.b200dock_mdn_load_encoder_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    lib.b200dock_vina.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200dock_mdn_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.b200dock_mdn_featurize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     if path is None:

@@ -72,19 +72,26 @@ def build_atom14_np(sequence, bb_t, bb_R, default_frame, rigid_pos, torsion_angl
     return out
 
 
-def _ca_walk(rng, n_res: int, radius: float) -> np.ndarray:
-    pts = [np.zeros(3)]
-    tries = 0
-    while len(pts) < n_res:
+def _ca_walk(rng, n_res: int, radius: float, budget: int = 40000) -> np.ndarray:
+    buf = np.zeros((n_res + 1, 3))
+    n, tries, spent = 1, 0, 0
+    while n < n_res:
+        spent += 1
+        if spent > budget:               # trapped walk (single-step back-up can cycle in a pocket of the sphere): start over
+            n, tries, spent = 1, 0, 0
+            radius *= 1.03
         d = rng.normal(size=3); d /= np.linalg.norm(d)
-        p = pts[-1] + 3.8 * d
-        ok = np.linalg.norm(p) < radius and all(np.linalg.norm(p - q) > 4.6 for q in pts[:-1])
+        p = buf[n - 1] + 3.8 * d
+        ok = np.linalg.norm(p) < radius
+        if ok and n > 1:                 # self-avoidance against all but the previous point
+            q = buf[:n - 1] - p
+            ok = bool((np.sqrt((q * q).sum(1)) > 4.6).all())
         tries += 1
         if ok or tries > 200:
-            if not ok and len(pts) > 2:  # dead end: back up
-                pts.pop(); tries = 0; continue
-            pts.append(p); tries = 0
-    pts = np.asarray(pts)
+            if not ok and n > 2:         # dead end: back up
+                n -= 1; tries = 0; continue
+            buf[n] = p; n += 1; tries = 0
+    pts = buf[:n_res].copy()
     return pts - pts.mean(0)
 
 

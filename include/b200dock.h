@@ -323,6 +323,34 @@ typedef struct {
 } B200MdnFeat;
 int b200dock_mdn_featurize(B200Handle* h, const B200MdnFeat* f, void* stream);
 
+/* Error correction of docked poses: replaces the per-pose `smina.static --minimize` subprocess of
+ * druglib/ops/smina/__init__.py:113-146 (smina_min_inplace; called by error_corrector, DiffBindFR/common/engines.py:304-322)
+ * and its `--score_only` variant.  One call handles all poses of ONE complex: AutoDock Vina 1.1.2 / smina default scoring function
+ * (what the binary evaluates) between the ligand heavy atoms and each pose's own pocket heavy atoms, plus the ligand's
+ * intramolecular pairs; mode 1 minimises it by BFGS over translation, rotation (about atom `root`) and torsion increments.
+ * Atom typing is an input (X-Score radius + flag bits 1 hydrophobe, 2 donor, 4 acceptor; diffbindfr_b200/vina_types.py).
+ * fp64 arithmetic, deterministic.  All pointers are DEVICE pointers; asynchronous on `stream`.
+ * Limits: n_lig <= 128, n_tors <= 58, n_rec <= 10000. */
+typedef struct {
+  int32_t n_pose, n_lig, n_rec, n_tors, root, max_steps, mode, reserved;   /* mode 0 score only, 1 minimise */
+  int64_t rec_pose_stride;       /* atoms between consecutive poses in rec_xyz; 0 = one rigid receptor for all poses */
+  const float* lig_xyz;          /* [n_pose][n_lig][3] */
+  const float* lig_radius; const uint8_t* lig_flags;      /* [n_lig] */
+  const float* rec_xyz;          /* [n_pose | 1][n_rec][3] */
+  const float* rec_radius; const uint8_t* rec_flags;      /* [n_rec] */
+  const int32_t* tors_axis;      /* [n_tors][2]: (atom on the root side, atom that moves); parents before children */
+  const uint8_t* tors_mask;      /* [n_tors][n_lig]: 1 = atom moves with this torsion */
+  const int32_t* pair_ptr;       /* [n_lig+1] CSR of the intramolecular pair list, every pair listed from both ends */
+  const int32_t* pair_idx;       /* [2 n_pairs] */
+  double n_rot;                  /* rotor count of the affinity normalisation 1 / (1 + 0.05846 n_rot) */
+  float* out_xyz;                /* [n_pose][n_lig][3] minimised poses (mode 1) */
+  double* out_energy;            /* [n_pose][4]: inter + intra, inter, intra (all with Vina's energy cap), affinity (kcal/mol) */
+  double* out_terms;             /* [n_pose][5] unweighted intermolecular term sums of the INPUT pose (`## ligand` line of
+                                    smina --score_only), or NULL */
+  int32_t* out_stats;            /* [n_pose][2]: BFGS steps, energy evaluations, or NULL */
+} B200Vina;
+int b200dock_vina(B200Handle* h, const B200Vina* v, void* stream);
+
 /* Introspection for tests / benchmarks: edge counts of the last evaluation
  * [E_ll, E_aa, E_al(=E_la), E_tor, E_sc], kernels launched by the last call, device time of the
  * dominant (tensor-product) kernel accumulated with CUDA events when profiling is enabled. */

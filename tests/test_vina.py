@@ -1,0 +1,153 @@
+"""Error-correction stage: oracle/vina.py and the CUDA kernel against outputs of the reference's own
+``smina.static`` binary on the reference's example complex (tests/golden/smina_3dbs.json, tools/make_golden_smina.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diffbindfr_b200 import correct, vina_types as vt
+from oracle import vina as ov
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "smina_3dbs.json")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    G = json.load(open(GOLD))
+    pk, lg = G["pocket"], G["ligand"]
+    rec64 = np.asarray(pk["xyz"], dtype=np.float64)
+    rec_xyz = rec64.astype(np.float32).astype(np.float64)
+    rR, rF = vt.receptor_types(pk["names"], pk["resnames"], pk["chains"], pk["resnums"], rec64)
+    lR, lF = vt.ligand_types(lg["elements"], lg["bonds"], lg["orders"], lg["n_h"])
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)           # the device takes fp32 inputs: same values on both sides
+    topo = ov.LigandTopology(len(lR), lg["bonds"], lg["orders"], root=0)
+    sysm = ov.VinaSystem(f32(lR), lF, topo, rec_xyz, f32(rR), rF)          # what the device sees (fp32 inputs)
+    sys64 = ov.VinaSystem(lR, lF, topo, rec64, rR, rF)                      # what the binary saw (decimal text)
+    return dict(G=G, rec_xyz=rec_xyz, rec64=rec64, rR=rR, rF=rF, lR=lR, lF=lF, topo=topo, sys=sysm, sys64=sys64,
+                poses=[f32(p["xyz"]) for p in G["poses"]], poses64=[np.asarray(p["xyz"], dtype=np.float64) for p in G["poses"]])
+
+
+def test_oracle_terms_affinity_and_intramolecular_match_the_binary(gold):
+    """All five unweighted term sums, the affinity (with Vina's per-atom energy cap and the rotor normalisation) and the
+    intramolecular energy of ``smina --score_only`` to the printed 5 decimals, for the crystal pose and five perturbed poses."""
+    for x, p in zip(gold["poses64"], gold["G"]["poses"]):
+        t = ov.inter_terms(x, gold["lR"], gold["lF"], gold["rec64"], gold["rR"], gold["rF"])
+        assert np.abs(t - np.asarray(p["terms"])).max() < 2e-5
+        assert abs(ov.affinity(gold["sys64"].inter(x, False, True), gold["topo"].n_rot) - p["affinity"]) < 2e-5
+        assert abs(gold["sys64"].intra(x, False, True) - p["intramolecular"]) < 2e-5
+
+
+def test_rotor_count_and_typing_rules(gold):
+    lg = gold["G"]["ligand"]
+    assert gold["topo"].n_rot == 5                                  # 1.2923 = 1 + 0.05846 * 5 in the binary's affinity
+    _, lF_implicit = vt.ligand_types(lg["elements"], lg["bonds"], lg["orders"], None)
+    assert np.array_equal(lF_implicit, gold["lF"])                  # valence-filled hydrogens == the explicit ones of the SDF
+    assert gold["lF"][29].tolist() == [0, 1, 0]                     # indazole N-H: donor, not an acceptor (3 connections, sp2)
+    tab = vt.residue_table()
+    assert tab["SER:OG"] == [0, 1, 1] and tab["LEU:CD1"] == [1, 0, 0] and tab["ALA:CA"] == [0, 0, 0] and tab["LYS:NZ"][1] == 1
+
+
+def test_host_topology_equals_oracle_topology(gold):
+    lg = gold["G"]["ligand"]
+    a, b = gold["topo"], correct.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"], root=0)
+    assert b.n_tors == a.n_rot and np.array_equal(a.pairs, b.pairs)
+    for t in range(b.n_tors):
+        assert tuple(b.tors_axis[t]) == (a.torsions[t][0], a.torsions[t][1])
+        assert np.where(b.tors_mask[t])[0].tolist() == a.torsions[t][2]
+    assert b.pair_ptr[-1] == 2 * len(a.pairs)
+
+
+def test_oracle_gradient_is_the_derivative_of_the_energy(gold):
+    S, topo, x = gold["sys"], gold["topo"], gold["poses"][1]
+
+    def f(x):
+        e1, g1 = S.inter(x, True, True); e2, g2 = S.intra(x, True, True)
+        return e1 + e2, g1 + g2
+    _, g = f(x)
+    gg = ov.generalized_gradient(x, g, topo)
+    for i in range(len(gg)):
+        st = np.zeros(len(gg)); st[i] = 1e-5
+        num = (f(ov.apply_increment(x, topo, st))[0] - f(ov.apply_increment(x, topo, -st))[0]) / 2e-5
+        assert abs(num - gg[i]) < 1e-5 * max(1.0, abs(gg[i]))
+
+
+def test_oracle_minimiser_lands_where_the_binary_lands(gold):
+    """Local minimisation on Vina's kinked landscape is optimiser dependent (the binary's own `--approximation` settings differ by
+    up to 0.25 kcal/mol and 0.3 A on these poses), so the bar is: energy never above the start, affinity within 0.35 kcal/mol of
+    the binary's converged run and the pose within 1 A RMSD of it."""
+    for k in (0, 2):
+        p = gold["G"]["poses"][k]
+        m = ov.minimize(gold["sys"], gold["poses"][k], max_steps=300)
+        xe = np.asarray(p["min_exact"]["xyz"])
+        assert m["energy"] <= gold["sys"].inter(gold["poses"][k], False, True) + gold["sys"].intra(gold["poses"][k], False, True)
+        assert abs(m["affinity"] - p["min_exact"]["affinity"]) < 0.35
+        assert np.sqrt(((m["x"] - xe) ** 2).sum(-1).mean()) < 1.0
+
+
+# ------------------------------------------------------------------------------------------------ device
+@pytest.fixture(scope="module")
+def corrector():
+    from diffbindfr_b200.engine import Engine
+    return correct.ErrorCorrector(Engine(0))
+
+
+@pytest.mark.gpu
+def test_cuda_score_matches_the_binary(gold, corrector):
+    lg = gold["G"]["ligand"]
+    topo = correct.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"], root=0)
+    X = np.stack(gold["poses"])
+    out = corrector.score(X, gold["rec_xyz"], (gold["lR"], gold["lF"]), (gold["rR"], gold["rF"]), topo)
+    for k, p in enumerate(gold["G"]["poses"]):
+        # against the binary: inputs reach the device as fp32 (4e-6 A at these coordinates), hence 1e-6 relative on the term sums
+        assert np.abs(out["terms"][k].cpu().numpy() - np.asarray(p["terms"])).max() < 2e-3
+        assert abs(float(out["affinity"][k]) - p["affinity"]) < 2e-4
+        assert abs(float(out["intra"][k]) - p["intramolecular"]) < 2e-4
+        # against the oracle on the same fp32 inputs: fp64 on both sides
+        t = ov.inter_terms(gold["poses"][k], np.float32(gold["lR"]).astype(np.float64), gold["lF"], gold["rec_xyz"],
+                           np.float32(gold["rR"]).astype(np.float64), gold["rF"])
+        assert np.abs(out["terms"][k].cpu().numpy() - t).max() < 1e-9 * np.abs(t).max()
+        assert abs(float(out["inter"][k]) - gold["sys"].inter(gold["poses"][k], False, True)) < 1e-9
+        assert abs(float(out["intra"][k]) - gold["sys"].intra(gold["poses"][k], False, True)) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_minimiser_equals_oracle_minimiser_and_tracks_the_binary(gold, corrector):
+    lg = gold["G"]["ligand"]
+    topo = correct.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"], root=0)
+    X = np.stack(gold["poses"])
+    # per-pose receptor blocks (the flexible-pocket layout): the same pocket repeated, results must equal the shared-receptor call
+    out = corrector.correct(X, gold["rec_xyz"], (gold["lR"], gold["lF"]), (gold["rR"], gold["rF"]), topo, max_steps=300)
+    rep = np.repeat(gold["rec_xyz"][None], len(X), 0)
+    out2 = corrector.correct(X, rep, (gold["lR"], gold["lF"]), (gold["rR"], gold["rF"]), topo, max_steps=300)
+    assert torch.equal(out["lig_xyz"], out2["lig_xyz"]) and torch.equal(out["energy"], out2["energy"])
+    start = corrector.score(X, gold["rec_xyz"], (gold["lR"], gold["lF"]), (gold["rR"], gold["rF"]), topo)
+    for k, p in enumerate(gold["G"]["poses"]):
+        x = out["lig_xyz"][k].double().cpu().numpy()
+        assert float(out["energy"][k]) <= float(start["energy"][k])
+        xe = np.asarray(p["min_exact"]["xyz"])
+        assert abs(float(out["affinity"][k]) - p["min_exact"]["affinity"]) < 0.35, k
+        assert np.sqrt(((x - xe) ** 2).sum(-1).mean()) < 1.0, k
+        # the reported energies belong to the returned pose.  Not tighter than one pair energy at the cutoff: Vina's potential is cut
+        # at 8 A where gauss2 is still -3.6e-3 kcal/mol, minimisation parks pairs right at that jump, and the fp32 output rounding
+        # (4e-6 A) can move one across
+        assert abs(gold["sys"].inter(x, False, True) + gold["sys"].intra(x, False, True) - float(out["energy"][k])) < 2e-2
+    # Same algorithm, fp64 on both sides, different summation order and exp(): the line search branches on energy differences at the
+    # kinks / cutoff jumps of the potential, so rounding-level differences can send the two down different (equally valid) paths.
+    # Bar: every pose ends within 0.1 kcal/mol and 0.5 A of the oracle's minimum, and most poses follow the identical path.
+    same = 0
+    for k in range(len(X)):
+        m = ov.minimize(gold["sys"], gold["poses"][k], max_steps=300)
+        de = abs(m["energy"] - float(out["energy"][k]))
+        rm = np.sqrt(((m["x"] - out["lig_xyz"][k].double().cpu().numpy()) ** 2).sum(-1).mean())
+        assert de < 0.1 and rm < 0.5, (k, de, rm)
+        same += int(de < 1e-3 and rm < 1e-2)
+    assert same >= len(X) // 2, same
+
+
+@pytest.mark.gpu
+def test_cuda_vina_rejects_bad_sizes(corrector):
+    topo = correct.LigandTopology(3, [(0, 1), (1, 2)])
+    with pytest.raises(RuntimeError):
+        corrector.score(np.zeros((1, 3, 3)), np.zeros((20000, 3)), (np.ones(3), np.zeros((3, 3))), (np.ones(20000), np.zeros((20000, 3))), topo)

@@ -1185,7 +1185,7 @@ int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t 
   const B200Batch& b = h->last_batch;
   const void* src = nullptr; size_t bytes = 0;
   if (what == B200_TAP_H_LIG) { src = h->h_lig.p; bytes = (size_t)b.N_l * HS * 4; }
-  else if (what == 7) { src = h->trace.p; bytes = h->trace.p ? (size_t)148 * 32 * 8 : 0; }
+  else if (what == 7) { src = h->trace.p; bytes = h->trace.p ? (size_t)B200_TRACE_WORDS * 8 : 0; }
   else if (what == B200_TAP_H_ATOM) { src = h->h_atom.p; bytes = (size_t)b.N_a * HS * 4; }
   else if (what == B200_TAP_EDGES) {
     if (arg < 0 || arg > 5) return B200_ERR_INVALID;
@@ -1230,8 +1230,8 @@ int b200dock_debug_set(B200Handle* h, int key, int value) {
   if (key == 0) { h->debug_layers = value; return B200_OK; }
   if (key == 1) {   // wait-cycle accounting of the fused conv kernel (mode 5): 148 CTAs x 32 counters, accumulated over launches
     CK(cudaSetDevice(h->device));
-    ENS(h->trace, (size_t)148 * 32 * 8);
-    CK(cudaMemset(h->trace.p, 0, (size_t)148 * 32 * 8));
+    ENS(h->trace, (size_t)B200_TRACE_WORDS * 8);
+    CK(cudaMemset(h->trace.p, 0, (size_t)B200_TRACE_WORDS * 8));
     h->trace_on = value != 0;
     return B200_OK;
   }

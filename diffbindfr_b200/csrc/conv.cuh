@@ -69,6 +69,14 @@ struct ConvArgs {
   float* part;              // [slots/32][2][HS]  partial sums of segments that cross a chunk boundary (tc_common.cuh)
   float inv_s1, inv_s2;     // fp16 mode: inverse power-of-two scales of the packed W1 / W2
 };
+// trace buffer (int64 words): 148 x 32 wait counters, then 16 event counters and 12 x B200_TL_N timeline stamps written by CTA 0
+#define B200_TL_N 6144
+#define B200_TRACE_WORDS (148 * 32 + 16 + 12 * B200_TL_N)
+// low-overhead stamp: every series has ONE writer thread, which keeps the running index in a register (loaded from / stored to the
+// counter slot at kernel start / end): a stamp is a clock read and a fire-and-forget store
+#define B200_TL_STAMP(L, series, idx, tag) do { const unsigned long long _c = (unsigned long long)clock64(); \
+    if ((idx) < B200_TL_N) reinterpret_cast<unsigned long long*>((L).trace)[148 * 32 + 16 + (size_t)(series) * B200_TL_N + (idx)] = (_c & ~0xffull) | (unsigned long long)((tag) & 0xff); \
+    ++(idx); } while (0)
 struct ConvLaunch { ConvArgs c[4]; int n; int dbg; long long* trace; };   // dbg / trace: timing experiments only (B200DOCK_DBG, debug_set(1))
 
 #define PRO_THREADS 256

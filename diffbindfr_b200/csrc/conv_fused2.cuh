@@ -49,6 +49,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   }
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking: has the phase of that parity completed?
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
 // TMA load into OWN shared memory, completion bytes signalled on the barrier at cluster address `bar_cluster`
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster) {
   asm volatile(
@@ -162,6 +171,10 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
     const long long t_begin = 0;
 #define TRW(i, stmt) do { stmt; } while (0)
 #endif
+#ifdef B200DOCK_TRACE
+    unsigned long long ti0 = 0, ti1 = 0, ti2 = 0;
+    if (tr && blockIdx.x == 0) { ti0 = L.trace[148 * 32 + 0]; ti1 = L.trace[148 * 32 + 1]; ti2 = L.trace[148 * 32 + 2]; }
+#endif
     uint64_t dhs[NST], dls[NST];
 #pragma unroll
     for (int s = 0; s < NST; ++s) {
@@ -191,8 +204,14 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           const uint32_t half = useq & 1;
           const uint32_t d_tmem = tmem_base + (uint32_t)(D0 + db.idx * BN);
           const bool last_unit = (unit + 1 == P.n_chunks);
+#ifdef B200DOCK_TRACE
+          if (tr && blockIdx.x == 0 && lane == 0) B200_TL_STAMP(L, 0, ti0, unit + 1);      // MMA warp reaches the accumulator wait
+#endif
           TRW(2, tc::mbar_wait_cluster(&d_empty[db.idx], db.par ^ 1));
           tc::fence_after();
+#ifdef B200DOCK_TRACE
+          if (tr && blockIdx.x == 0 && lane == 0) B200_TL_STAMP(L, 1, ti1, unit + 1);      // accumulator free: issue begins
+#endif
 #pragma unroll
           for (int ka = 0; ka < KATOMS; ++ka) {
             const int s = half ? KATOMS + ka : ka;
@@ -217,11 +236,17 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
             }
             __syncwarp();
           }
+#ifdef B200DOCK_TRACE
+          if (tr && blockIdx.x == 0 && lane == 0) B200_TL_STAMP(L, 2, ti2, unit + 1);      // all MMAs of the unit issued, commits queued
+#endif
           if (half) bpar1 ^= 1; else bpar0 ^= 1;
           tc::advance(db, 2);
         }
       }
     }
+#ifdef B200DOCK_TRACE
+    if (tr && blockIdx.x == 0 && lane == 0) { L.trace[148 * 32 + 0] = ti0; L.trace[148 * 32 + 1] = ti1; L.trace[148 * 32 + 2] = ti2; }
+#endif
     if (tr && lane == 0) {
       tw[7] = clock64() - t_begin;
       for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + i), (unsigned long long)tw[i]);
@@ -247,6 +272,8 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
     // fold-warp accounting (L.trace slots 8..15): a_empty wait, xin gather+store, x1 gather, D1 wait, H1 conversion, fold d_full waits, fold compute, total
     long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #ifdef B200DOCK_TRACE
+    unsigned long long ti0 = 0, ti1 = 0;
+    if (L.trace != nullptr && blockIdx.x == 0) { ti0 = L.trace[148 * 32 + 3 + q]; ti1 = L.trace[148 * 32 + 7 + q]; }
     const bool tr = L.trace != nullptr;
     const long long t_begin = tr ? clock64() : 0;
     long long tmark = 0;
@@ -423,6 +450,9 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           tc::mbar_wait_cluster(&d_full[db.idx], db.par);
           TRE_END(5);
           tc::fence_after();
+#ifdef B200DOCK_TRACE
+          if (tr && blockIdx.x == 0 && lane == 0) B200_TL_STAMP(L, 3 + q, ti0, ch + 1);    // fold warp q sees the accumulator full
+#endif
           const uint32_t taddr = lane_base + (uint32_t)(D0 + db.idx * BN);
           const float zs = C.inv_s2 / shh;             // D = (shh H1)(s2 W2)^T
           if (dbg & 2) { }
@@ -431,6 +461,9 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
           tc::fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_cluster(d_empty0[db.idx]);
+#ifdef B200DOCK_TRACE
+          if (tr && blockIdx.x == 0 && lane == 0) B200_TL_STAMP(L, 7 + q, ti1, pa.Wd == 48 ? 1 : 2);   // fold warp q released it
+#endif
           tc::advance(db, 2);
           bool last = (ch + 1 == P.n_chunks) || (P.paths[P.chunk_path[ch + 1]].out_off != pa.out_off);
           if (last && !(dbg & 1)) {                      // message block complete: segmented sum over the warp's 32 edges
@@ -449,6 +482,9 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
         }
       }
     }
+#ifdef B200DOCK_TRACE
+    if (tr && blockIdx.x == 0 && lane == 0) { L.trace[148 * 32 + 3 + q] = ti0; L.trace[148 * 32 + 7 + q] = ti1; }
+#endif
     if (tr && warp == 4 && lane == 0) {
       te[7] = clock64() - t_begin;
       for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + 8 + i), (unsigned long long)te[i]);

@@ -41,15 +41,6 @@ constexpr size_t V3_SMEM = 1024 + (size_t)V3_NST * 2 * V3_B_PART + 512 + (size_t
                          + (size_t)V3_NZ * 24 * 128 * 4 + (size_t)4 * B200_MAX_CHUNKS * sizeof(UnitDesc);
 
 namespace tc {
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking: has the phase of that parity completed?
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return done != 0;
-}
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
   asm volatile(

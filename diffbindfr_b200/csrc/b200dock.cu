@@ -56,7 +56,7 @@ struct ConvW {                  // views into the device weight blob
 
 // conv kernels: 0 exact fp32 SIMT (192-column units), 5 fused tcgen05 single CTA, 6 fused tcgen05 CTA pairs + fused scatter (144),
 // 10 the pair kernel re-pipelined over two A buffers with 96-column units (no tile-transition bubble)
-inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6 || k == 10; }
+inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6 || k == 10 || k == 11; }
 inline int variant_of_kernel(int k) { return k == 0 ? 0 : (k == 10 ? 2 : 1); }
 inline bool kernel_keeps_msg(int k) { return k == 0 || k == 5; }
 
@@ -230,6 +230,11 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const Fused16Extra& F, cudaStr
     static const int dbg = getenv("B200DOCK_DBG") ? atoi(getenv("B200DOCK_DBG")) : 0;   // honoured by the -DB200DOCK_TRACE build only
     ConvLaunch L2 = L; L2.dbg = dbg;
     rc = launch_conv_fused16x2(L2, F, h->tp_grid, st);
+  }
+  else if (k == 11) {
+    static const int dbg = getenv("B200DOCK_DBG") ? atoi(getenv("B200DOCK_DBG")) : 0;
+    ConvLaunch L2 = L; L2.dbg = dbg;
+    rc = launch_conv_fused16x2(L2, F, h->tp_grid, st, true);
   }
   else if (k == 5) rc = launch_conv_fused16(L, F, h->tp_grid, st);
   else {
@@ -534,7 +539,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   *out = h;
   h->device = device;
   h->cfg = *cfg;
-  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs, 10 re-pipelined pair kernel)");
+  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs, 10 re-pipelined pair kernel, 11 pair kernel with a gather/convert warpgroup)");
   h->variant = variant_of_kernel(cfg->conv_kernel);
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;

@@ -16,7 +16,8 @@
 
 #define F2_NST 6
 #define F2_HB 72                      // B rows (weight columns) per CTA per unit
-constexpr size_t F2_SMEM = 1024 + (size_t)F2_NST * 2 * F2_HB * 128 + (size_t)128 * F_X1S * 4 + 512 + (size_t)4 * 32 * SCAT_STRIDE * 4;
+constexpr size_t F2_SMEM = 1024 + (size_t)F2_NST * 2 * F2_HB * 128 + (size_t)128 * F_X1S * 4 + 512 + (size_t)4 * 32 * SCAT_STRIDE * 4 + 2 * 128 * 4;
+#define F2G_THREADS 384              // split-role variant (kernel 11): + one warpgroup that gathers / converts the edge input and H1
 
 namespace tc {
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -78,7 +79,38 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
 }
 }  // namespace tc
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+// This cluster's tiles (pairs of 128-edge tiles) in processing order, across the convs of the launch
+struct TileSeq { int ci, pair, npair, ntile, pairs_before; };
+__device__ __forceinline__ bool seq_next_conv(const ConvLaunch& L, int cid, int nclus, TileSeq& s) {
+  for (++s.ci; s.ci < L.n; ++s.ci) {
+    const int ntile = (*L.c[s.ci].n_edges + TILE_E - 1) / TILE_E;
+    const int npair = (ntile + 1) >> 1;
+    const int first = (int)((cid + nclus - (s.pairs_before % nclus)) % nclus);
+    s.pairs_before += npair;
+    if (first < npair) { s.pair = first; s.npair = npair; s.ntile = ntile; return true; }
+  }
+  return false;
+}
+__device__ __forceinline__ bool seq_begin(const ConvLaunch& L, int cid, int nclus, TileSeq& s) {
+  s.ci = -1; s.pair = 0; s.npair = 0; s.ntile = 0; s.pairs_before = 0;
+  return seq_next_conv(L, cid, nclus, s);
+}
+__device__ __forceinline__ bool seq_next(const ConvLaunch& L, int cid, int nclus, TileSeq& s) {
+  s.pair += nclus;
+  if (s.pair < s.npair) return true;
+  return seq_next_conv(L, cid, nclus, s);
+}
+
+// SPLIT = false: kernel 6 (8 warps: the four epilogue warps gather, convert and fold).
+// SPLIT = true : kernel 11 (12 warps).  tools/timeline.py showed that kernel 6 runs its W2 units at the ideal 2088 cycles but loses
+// ~30 k cycles per tile between the last unit of one tile and the first W2 unit of the next: index loads -> scatter context ->
+// row gather -> fp16 split -> tensor-memory store -> first-FC MMAs -> H1 conversion, all serialised in the fold warps.  Here a third
+// warpgroup (G, warps 8-11) gathers and converts the NEXT tile's edge input into registers (packed fp16 hi / lo) while the
+// current tile is still being multiplied, stores it the moment the A operand is free, and also converts H1 (one tensor-memory
+// pass, D1 released immediately); the fold warps (F, warps 4-7) prefetch their node rows / scatter context for the next tile
+// right after their last fold and otherwise only fold and scatter.  Same arithmetic, bit-identical results.
+template <bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SPLIT ? F2G_THREADS : TC_THREADS, 1)
 k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
   constexpr int BN = F16_BN, NST = F2_NST, HB = F2_HB;
   constexpr int KATOMS = 3;                      // K = 192 halves = 3 swizzle atoms of 64 fp16
@@ -95,6 +127,8 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
   uint64_t* d_full = bars + 3 + 2 * NST;  uint64_t* d_empty = d_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
   float* scat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [4 warps][32][SCAT_STRIDE] scatter scratch
+  float* shh_s = scat + 4 * 32 * SCAT_STRIDE;                                       // [2][128] H1 row scales, G -> F (SPLIT)
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);                    // [2] (SPLIT)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = tc::cluster_ctarank();
@@ -102,7 +136,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
   if (threadIdx.x == 0) {
     tc::mbar_init(x_full, 8); tc::mbar_init(h_full, 8); tc::mbar_init(a_empty, 1);
     for (int s = 0; s < NST; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&d_full[b], 1); tc::mbar_init(&d_empty[b], 8); tc::mbar_init(&s_full[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -115,6 +149,8 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
   tc::fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  if (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // registers to where they are needed: 56 / 232 / 208 per thread (sum < 512, see conv_v3.cuh)
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs: own 72 rows)
     if (lane == 0)
@@ -252,7 +288,14 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
       for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(L.trace + blockIdx.x * 32 + i), (unsigned long long)tw[i]);
     }
 #undef TRW
-  } else if (warp >= 4) {
+  }
+  } else if (SPLIT && warp >= 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+#include "conv_fused2_g.inc"
+  } else if (SPLIT) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+#include "conv_fused2_f.inc"
+  } else {
     // ================================================== gather / H1 / epilogue warps (thread = edge), both CTAs
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -503,10 +546,11 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
 }
 
 static inline int conv_fused2_init() {
-  return cudaFuncSetAttribute(k_conv_fused16x2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM) == cudaSuccess ? 0 : 1;
+  if (cudaFuncSetAttribute(k_conv_fused16x2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM) != cudaSuccess) return 1;
+  return cudaFuncSetAttribute(k_conv_fused16x2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F2_SMEM) == cudaSuccess ? 0 : 1;
 }
 
-static inline int launch_conv_fused16x2(const ConvLaunch& L, const Fused16Extra& X, int grid, cudaStream_t st) {
+static inline int launch_conv_fused16x2(const ConvLaunch& L, const Fused16Extra& X, int grid, cudaStream_t st, bool split = false) {
   if (!g_encode) return 1;
   FusedMaps maps;
   memset(&maps, 0, sizeof maps);
@@ -516,6 +560,7 @@ static inline int launch_conv_fused16x2(const ConvLaunch& L, const Fused16Extra&
     if (tc_make_map16(&maps.w1[i], X.W1hi[i], 192, F2_HB)) return 4;
     if (tc_make_map16(&maps.w1_lo[i], X.W1lo[i], 192, F2_HB)) return 5;
   }
-  k_conv_fused16x2<<<grid & ~1, TC_THREADS, F2_SMEM, st>>>(L, maps);
+  if (split) k_conv_fused16x2<true><<<grid & ~1, F2G_THREADS, F2_SMEM, st>>>(L, maps);
+  else k_conv_fused16x2<false><<<grid & ~1, TC_THREADS, F2_SMEM, st>>>(L, maps);
   return cudaGetLastError() == cudaSuccess ? 0 : 6;
 }

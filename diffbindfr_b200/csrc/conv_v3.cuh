@@ -97,28 +97,6 @@ __device__ __forceinline__ void fold_w12(const float* v, int nu, const float* z 
 }
 }  // namespace tc
 
-// This cluster's tiles (pairs of 128-edge tiles) in processing order, across the convs of the launch
-struct TileSeq { int ci, pair, npair, ntile, pairs_before; };
-__device__ __forceinline__ bool seq_next_conv(const ConvLaunch& L, int cid, int nclus, TileSeq& s) {
-  for (++s.ci; s.ci < L.n; ++s.ci) {
-    const int ntile = (*L.c[s.ci].n_edges + TILE_E - 1) / TILE_E;
-    const int npair = (ntile + 1) >> 1;
-    const int first = (int)((cid + nclus - (s.pairs_before % nclus)) % nclus);
-    s.pairs_before += npair;
-    if (first < npair) { s.pair = first; s.npair = npair; s.ntile = ntile; return true; }
-  }
-  return false;
-}
-__device__ __forceinline__ bool seq_begin(const ConvLaunch& L, int cid, int nclus, TileSeq& s) {
-  s.ci = -1; s.pair = 0; s.npair = 0; s.ntile = 0; s.pairs_before = 0;
-  return seq_next_conv(L, cid, nclus, s);
-}
-__device__ __forceinline__ bool seq_next(const ConvLaunch& L, int cid, int nclus, TileSeq& s) {
-  s.pair += nclus;
-  if (s.pair < s.npair) return true;
-  return seq_next_conv(L, cid, nclus, s);
-}
-
 // Unit order seen by every role (useq counts units, D buffer = useq & 1, its use number = useq >> 1):
 //   W1a(T0) W1b(T0) | W2(T0,0) .. W2(T0,n-3) W1a(T1) W1b(T1) W2(T0,n-2) W2(T0,n-1) | W2(T1,0) .. | ...
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V3_THREADS, 1)

@@ -13,9 +13,9 @@ from helpers import conditioning, load_golden, rmsd
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,5,6,10").split(",") if k]
+KERNELS = [int(k) for k in os.environ.get("B200DOCK_TEST_KERNELS", "0,5,6,10,11").split(",") if k]
 # fp32 score tolerance: |cuda - oracle_fp32| <= RTOL * max|oracle| (fp32 oracle itself is ~2e-6 from fp64)
-RTOL = {0: 2e-4, 5: 2e-4, 6: 2e-4, 10: 2e-4}
+RTOL = {0: 2e-4, 5: 2e-4, 6: 2e-4, 10: 2e-4, 11: 2e-4}
 
 
 @pytest.fixture(scope="module")
@@ -215,13 +215,13 @@ def test_pair_kernel_bit_identical_to_single_cta(sd):
     (message rows + k_msg_scatter) and the same sequential segment sums: identical bits, including odd tile counts (the peer
     CTA recomputes the last tile and reduces nothing).  Mode 10 (two A buffers, 96-column units, direct x1 loads, separate
     gather / fold warpgroups) changes the pipeline, not the arithmetic: identical bits as well."""
-    e5, e6, e10 = make_engine(5, sd), make_engine(6, sd), make_engine(10, sd)
+    e5, e6, e10, e11 = make_engine(5, sd), make_engine(6, sd), make_engine(10, sd), make_engine(11, sd)
     for wl, seed in ((synth.WORKLOADS["tiny"], 3), (dict(n_complex=1, n_poses=3, n_res=36, n_lig=30), 5),
                      (dict(n_complex=3, n_poses=2, n_res=(20, 60), n_lig=(10, 40)), 6)):
         b = synth.make_batch(**wl, seed=seed)
         c = conditioning(b)
         r5 = run_score(e5, b, c)
-        for eng in (e6, e10):
+        for eng in (e6, e10, e11):
             for a, r in zip(run_score(eng, b, c), r5):
                 assert torch.equal(a, r)
 
@@ -337,7 +337,7 @@ def _sorted_rows(pairs, feats):
     return rows[order]
 
 
-@pytest.mark.parametrize("kernel", [5, 6, 10])
+@pytest.mark.parametrize("kernel", [5, 6, 10, 11])
 def test_embedding_layers_match_oracle_taps(sd, kernel):
     """Layer-level parity: node embeddings (SimpleLinear / AtomEncoder), edge embeddings (GaussianSmearing +
     SimpleLinear) and spherical harmonics of every conv graph against the oracle's intermediate tensors; then the node features
@@ -451,7 +451,7 @@ def test_bench_batch_trajectory_against_oracle_fixture(sd):
     assert batch_checksum(b) == g["batch_checksum"]
     sch = schedule.make_schedule()[:g["steps"]]
     z = bench_noise(b, g["steps"], g["noise_seed"])
-    for kernel in (6, 10):
+    for kernel in (6, 10, 11):
         eng = make_engine(kernel, sd)
         lig, a14, lig_traj, _ = eng.sample(b, sch, z, trajectory=True)
         torch.cuda.synchronize()

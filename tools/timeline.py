@@ -8,7 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diffbindfr_b200 import synth, weights, schedule
 from diffbindfr_b200.engine import Engine
 b = synth.make_batch(**synth.WORKLOADS["cfgA"], seed=0)
-eng = Engine(0, conv_kernel=6)
+KERNEL = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+eng = Engine(0, conv_kernel=KERNEL)
 eng.load_state_dict(weights.random_state_dict(0))
 sch = schedule.make_schedule()[10:12]
 B, n_tor, n_sc = b["num_graphs"], int(b["tor_edge_mask"].sum()), int(b["sc_torsion_edge_mask"].sum())
@@ -26,6 +27,33 @@ tag = S[0] & 0xff
 T = [(s & ~0xff).astype(np.int64) for s in S]
 w2 = tag != 0                                   # W2 units (the W1 unit of a tile has tag 0)
 A, Bg, Cc = T[0][w2], T[1][w2], T[2][w2]
+# tile structure from the MMA warp alone (works for every pair-kernel variant)
+starts = np.where(tag == 0)[0]
+ib = T[1]
+rows = []
+for s0, s1 in zip(starts[:-1], starts[1:]):
+    nu = s1 - s0 - 1
+    seg = ib[s0:s1 + 1]
+    if (np.diff(seg) <= 0).any() or (np.diff(seg) > 400000).any(): continue
+    rows.append((nu, seg[1] - seg[0], seg[2] - seg[1] if nu > 1 else 0, np.median(np.diff(seg[1:-1])) if nu > 2 else 0, seg[-1] - seg[-2], seg[-1] - seg[0]))
+rows = np.array(rows, dtype=np.float64)
+for nu in sorted(set(rows[:, 0].astype(int))):
+    r = rows[rows[:, 0] == nu]
+    print(f"tiles with {nu:2d} units: {len(r):3d}   W1 begin -> unit0 begin {np.median(r[:,1]):7.0f}   unit0 -> unit1 {np.median(r[:,2]):6.0f}   mid interval {np.median(r[:,3]):6.0f}"
+          f"   last unit begin -> next W1 begin {np.median(r[:,4]):7.0f}   tile span {np.median(r[:,5]):8.0f}  ideal {(nu + 1) * 2088}")
+# the first units of a tile in detail: per unit (reach accumulator wait -> free), (free -> all issued), (issued -> next unit reaches its wait)
+det = {k: [] for k in range(-1, 4)}
+for s0, s1 in zip(starts[:-1], starts[1:]):
+    if s1 - s0 < 8: continue
+    for k in range(-1, 4):
+        i = s0 + 1 + k
+        det[k].append((T[1][i] - T[0][i], T[2][i] - T[1][i], T[0][i + 1] - T[2][i], T[0][i] - T[2][i - 1] if i > 0 else 0))
+for k in range(-1, 4):
+    a = np.array(det[k], dtype=np.float64)
+    print(("W1    " if k < 0 else f"unit {k}"), " before-wait gap", np.median(a[:, 3]), " accumulator wait", np.median(a[:, 0]), " issue", np.median(a[:, 1]))
+tot = rows[:, 5].sum(); ideal = ((rows[:, 0] + 1) * 2088).sum()
+print("tensor-busy share over these tiles (ideal / span):", ideal / tot)
+if KERNEL != 6: sys.exit(0)
 n = min(len(A), *(len(T[i]) for i in range(3, 11)))
 A, Bg, Cc = A[:n], Bg[:n], Cc[:n]
 seen = np.stack([T[3 + q][:n] for q in range(4)]); rel = np.stack([T[7 + q][:n] for q in range(4)])

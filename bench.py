@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfgA", choices=sorted(synth.JOBS))
-    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "6")))
+    ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "11")))
     ap.add_argument("--batch-size", type=int, default=320, help="samples per device batch of the multi-complex workloads")
     ap.add_argument("--complexes", type=int, default=0, help="override the number of complexes of a multi-complex workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")

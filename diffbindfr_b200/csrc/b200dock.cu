@@ -92,7 +92,7 @@ struct B200Handle {
   int tp_grid = 148;
   std::vector<float> cg_dense; int atom14_group[21 * 14];
   // side stream: independent small kernels (graph families, ligand vs pocket node updates, centre head) run concurrently
-  bool nvtx = false;
+  bool nvtx = false, warp_node_update = false;
   int* host_meta = nullptr; bool deferred_check = false; size_t feat_smem = 48 * 1024, vina_smem = 48 * 1024;
   Buf ex_in, ex_pin, ex_out[32];   // batch assembly: staged base batch (device / pinned) and the expanded arrays
   Buf trace; bool trace_on = false;
@@ -383,11 +383,13 @@ int score_device(B200Handle* h, const B200Batch& b, const B200Cond& c, float* tr
     U.src[0] = agg_src(h->cw[0]); U.ln[0] = h->convw[0 * 6 + l].ln;
     U.src[1] = agg_src(h->cw[2]); U.ln[1] = h->convw[2 * 6 + l].ln;
     cudaStream_t s2 = side_fork(h, st);                                  // ligand and pocket node updates are independent
-    k_node_update<<<grid_for(b.N_l, 8, 148 * 8), 256, 0, st>>>(U);
+    if (h->warp_node_update) k_node_update_warp<<<grid_for(b.N_l, 8, 148 * 8), 256, 0, st>>>(U);
+    else k_node_update<<<cdiv((long long)b.N_l * h->dplans[plan].n_blocks, 128), 128, 0, st>>>(U);   // one thread per (node, irreps block)
     U.N = b.N_a; U.h = ha;
     U.src[0] = agg_src(h->cw[1]); U.ln[0] = h->convw[1 * 6 + l].ln;
     U.src[1] = agg_src(h->cw[3]); U.ln[1] = h->convw[3 * 6 + l].ln;
-    k_node_update<<<grid_for(b.N_a, 8, 148 * 8), 256, 0, s2>>>(U);
+    if (h->warp_node_update) k_node_update_warp<<<grid_for(b.N_a, 8, 148 * 8), 256, 0, s2>>>(U);
+    else k_node_update<<<cdiv((long long)b.N_a * h->dplans[plan].n_blocks, 128), 128, 0, s2>>>(U);
     side_join(h, st);
     h->launches += 2;
   }
@@ -561,6 +563,12 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
     d.in_dim = s.in_dim; d.sh_dim = s.sh_dim; d.out_dim = s.out_dim; d.z_numel = s.z_numel; d.n_cols = s.n_cols;
     d.n_blocks = s.n_blocks;
     for (int i = 0; i < B200_MAX_BLOCKS; ++i) d.blocks[i] = s.blocks[i];
+    if (p < B200_PLAN_TOR)                            // k_node_update: one thread per (node, irreps block), float4 rows
+      for (int i = 0; i < s.n_blocks; ++i) {
+        const B200Block& bl = s.blocks[i];
+        if (!((bl.dim == 1 && bl.mul == 48) || (bl.dim == 3 && bl.mul == 12)) || (bl.off & 3))
+          FAIL(B200_ERR_INVALID, "conv layer output irreps must be blocks of 48 scalars / 12 vectors at 16-byte aligned offsets");
+      }
     d.n_chunks = s.n_chunks;
     if (s.n_chunks > B200_MAX_CHUNKS) FAIL(B200_ERR_INVALID, "too many weight chunks in a conv plan");
     for (int i = 0; i < s.n_chunks; ++i) { d.chunk_col[i] = s.chunk_col[i]; d.chunk_n[i] = s.chunk_n[i]; d.chunk_path[i] = s.chunk_path[i]; }
@@ -1233,6 +1241,7 @@ int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t 
 int b200dock_debug_set(B200Handle* h, int key, int value) {
   if (!h) return B200_ERR_INVALID;
   if (key == 0) { h->debug_layers = value; return B200_OK; }
+  if (key == 2) { h->warp_node_update = value != 0; return B200_OK; }
   if (key == 1) {   // wait-cycle accounting of the fused conv kernel (mode 5): 148 CTAs x 32 counters, accumulated over launches
     CK(cudaSetDevice(h->device));
     ENS(h->trace, (size_t)B200_TRACE_WORDS * 8);

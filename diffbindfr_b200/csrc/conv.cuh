@@ -408,8 +408,136 @@ __device__ __forceinline__ void ln_row(const DevPlan& P, LnParams ln, float* row
   __syncwarp();
 }
 
+// h[n] += LN_0(mean_0) + LN_1(mean_1)  (tpscore.py:513-516).
+// One THREAD per (node, irreps block): an irreps block of a row is 48 or 36 contiguous floats, so its LayerNorm statistics are plain
+// serial sums in registers - no warp shuffles, no column masks.  (The first two versions used one warp per node with lanes over
+// columns: ~2600 issued instructions per node, 85 us per pocket update and 0.53 ms per denoising step on the critical path
+// between the conv launches; ncu r02: issue-latency bound at 16 warps / SM.)  Threads are ordered block-major, so a warp is
+// uniform in the block it handles.
+// sum of 32 lane values in the order of warp_sum's xor butterfly (16, 8, 4, 2, 1)
+__device__ __forceinline__ float butterfly32(const float* p) {
+  float s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+  for (int l = 0; l < 16; ++l) s16[l] = p[l] + p[l + 16];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) s8[l] = s16[l] + s16[l + 8];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) s4[l] = s8[l] + s8[l + 4];
+  s2[0] = s4[0] + s4[2]; s2[1] = s4[1] + s4[3];
+  return s2[0] + s2[1];
+}
+
+template <int DIM>
+__device__ __forceinline__ void ln_block_thread(const AggSrc& S, const LnParams& ln, const B200Block& bl, int n, float* acc) {
+  constexpr int MUL = DIM == 1 ? 48 : 12;
+  constexpr int LEN = MUL * DIM;
+  const int cnt = S.counts[n], sb = S.seg[n];
+  const float den = (float)max(cnt, 1);
+  float x[LEN];
+  if (cnt <= 0) {
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) x[j] = 0.0f;
+  } else {
+    const int c0 = sb >> 5, c1 = (sb + cnt - 1) >> 5;
+    if (c0 == c1) {                                      // the node's own sum row
+      const float4* r = reinterpret_cast<const float4*>(S.agg + (size_t)n * HS + bl.off);
+#pragma unroll
+      for (int j = 0; j < LEN / 4; ++j) { const float4 f = r[j]; x[4 * j] = f.x; x[4 * j + 1] = f.y; x[4 * j + 2] = f.z; x[4 * j + 3] = f.w; }
+    } else {                                             // segment crosses 32-slot chunks: partial rows in chunk order
+      const float4* r = reinterpret_cast<const float4*>(S.part + ((size_t)c0 * 2 + 1) * HS + bl.off);
+#pragma unroll
+      for (int j = 0; j < LEN / 4; ++j) { const float4 f = r[j]; x[4 * j] = f.x; x[4 * j + 1] = f.y; x[4 * j + 2] = f.z; x[4 * j + 3] = f.w; }
+      for (int cc = c0 + 1; cc <= c1; ++cc) {
+        const float4* p = reinterpret_cast<const float4*>(S.part + ((size_t)cc * 2) * HS + bl.off);
+#pragma unroll
+        for (int j = 0; j < LEN / 4; ++j) { const float4 f = p[j]; x[4 * j] += f.x; x[4 * j + 1] += f.y; x[4 * j + 2] += f.z; x[4 * j + 3] += f.w; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) x[j] = x[j] / den;     // scatter 'mean' with clamp(min=1) on the count (tpscore.py:190)
+  }
+  // equivariant LayerNorm of this block (tpscore.py:20-107).  The sums reproduce, term by term, the order of the warp-per-node
+  // form (ln_row: lane partial sums over u = lane, lane + 32, then the xor butterfly of warp_sum), which keeps this kernel
+  // bit-identical to it - the committed 40 x 20 oracle trajectory is compared at 1e-4 A, where summation order is visible.
+  float m[DIM];
+  {
+    float p[DIM][32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      float a[DIM];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) a[i] = 0.0f;
+#pragma unroll
+      for (int u = l; u < MUL; u += 32)
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) a[i] += x[u * DIM + i];
+#pragma unroll
+      for (int i = 0; i < DIM; ++i) p[i][l] = a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) m[i] = butterfly32(p[i]) / (float)MUL;
+  }
+  float nrm;
+  {
+    float p[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      float acc_l = 0.0f;
+#pragma unroll
+      for (int u = l; u < MUL; u += 32) {
+        const float sh = __ldg(ln.shift + bl.irr_off + u);
+        float v0 = fmaf(-m[0], sh, x[u * DIM]), sq;
+        if (DIM == 3) {
+          const float v1 = fmaf(-m[1], sh, x[u * DIM + 1]), v2 = fmaf(-m[DIM - 1], sh, x[u * DIM + 2]);
+          sq = fmaf(v0, v0, fmaf(v1, v1, __fmul_rn(v2, v2)));           // the contraction nvcc picks for ln_row's `sq += v1 * v1 + v2 * v2`
+        } else sq = __fmul_rn(v0, v0);
+        acc_l = __fadd_rn(acc_l, __fdiv_rn(sq, (float)DIM));
+      }
+      p[l] = acc_l;
+    }
+    nrm = butterfly32(p) / (float)MUL;
+  }
+  const float scl = 1.0f / sqrtf(nrm + 1e-5f);
+#pragma unroll
+  for (int u = 0; u < MUL; ++u) {
+    const float sh = __ldg(ln.shift + bl.irr_off + u), wt = __ldg(ln.weight + bl.irr_off + u);
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      const float fld = fmaf(-m[i], sh, x[u * DIM + i]);
+      float v = __fmul_rn(fld, __fmul_rn(scl, wt));
+      if (bl.bias_off >= 0) v += __ldg(ln.bias + bl.bias_off + u);
+      acc[u * DIM + i] = __fadd_rn(acc[u * DIM + i], v);   // no contraction with the product above (the warp-per-node form added a stored row)
+    }
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void node_block_thread(const NodeUpdateArgs& A, const B200Block& bl, int n) {
+  constexpr int LEN = DIM == 1 ? 48 : 36;
+  float acc[LEN];
+  float4* hp = reinterpret_cast<float4*>(A.h + (size_t)n * HS + bl.off);
+#pragma unroll
+  for (int j = 0; j < LEN / 4; ++j) { const float4 f = hp[j]; acc[4 * j] = f.x; acc[4 * j + 1] = f.y; acc[4 * j + 2] = f.z; acc[4 * j + 3] = f.w; }
+  ln_block_thread<DIM>(A.src[0], A.ln[0], bl, n, acc);
+  ln_block_thread<DIM>(A.src[1], A.ln[1], bl, n, acc);
+#pragma unroll
+  for (int j = 0; j < LEN / 4; ++j) hp[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+}
+
+// blocks are 48 x (dim 1) or 12 x (dim 3) with 16-byte aligned offsets (0, 48, 84, 120): checked on the host (node_update_supported)
+__global__ void __launch_bounds__(128) k_node_update(NodeUpdateArgs A) {
+  const DevPlan& P = c_plans[A.plan];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = t / A.N, n = t - b * A.N;               // block-major: a warp handles one irreps block of 32 consecutive nodes
+  if (b >= P.n_blocks) return;
+  const B200Block bl = P.blocks[b];
+  if (bl.dim == 1) node_block_thread<1>(A, bl, n);
+  else node_block_thread<3>(A, bl, n);
+}
+
+// The warp-per-node form (cross-check of the kernel above: b200dock_debug_set(h, 2, 1); bit-identical, 5x slower)
 // h[n] += LN_0(mean_0) + LN_1(mean_1)  (tpscore.py:513-516); one warp per node
-__global__ void __launch_bounds__(256) k_node_update(NodeUpdateArgs A) {
+__global__ void __launch_bounds__(256) k_node_update_warp(NodeUpdateArgs A) {
   __shared__ float rows[8][HS];
   const DevPlan& P = c_plans[A.plan];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

@@ -37,7 +37,7 @@ def job_samples(complexes: Sequence[Dict[str, np.ndarray]], n_poses: int) -> Lis
 class Docker:
     """Sampler + MDN scorer of one device."""
 
-    def __init__(self, device: int, sd: Dict[str, torch.Tensor], mdn_sd: Optional[Dict[str, torch.Tensor]] = None, conv_kernel: int = 6):
+    def __init__(self, device: int, sd: Dict[str, torch.Tensor], mdn_sd: Optional[Dict[str, torch.Tensor]] = None, conv_kernel: int = 11):
         self.eng = Engine(device, conv_kernel=conv_kernel)
         self.eng.load_state_dict(sd)
         self.scorer = None

@@ -99,7 +99,7 @@ _EXPECTED_CFG = dict(ns=spec.NS, nv=spec.NV, sh_lmax=2, lig_cutoff=5, atom_cutof
 class TensorProductModel(_DropE3nnBuffers, nn.Module):
     """B200 implementation of the SE(3)-equivariant score network (same state_dict as the reference)."""
 
-    def __init__(self, cfg=None, conv_kernel: int = 6, device: Optional[int] = None):
+    def __init__(self, cfg=None, conv_kernel: int = 11, device: Optional[int] = None):
         super().__init__()
         self.cfg = cfg
         if cfg is not None:
@@ -195,7 +195,7 @@ class DiffBindFR(nn.Module):
             if isinstance(dm, nn.Module):
                 self.diffusion_model = dm
             else:
-                self.diffusion_model = TensorProductModel(_get(dm, "cfg"), conv_kernel=int(_get(dm, "conv_kernel", 6)))
+                self.diffusion_model = TensorProductModel(_get(dm, "cfg"), conv_kernel=int(_get(dm, "conv_kernel", 11)))
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.pretrain, self.init_cfg = pretrained, init_cfg
         self._schedule = None

@@ -371,7 +371,8 @@ int b200dock_tp_kernel_time_ms(B200Handle* h, double* ms, int64_t* launches);
                                  every target, [T] = slots, [T+1] = real edges), 6 centre msg [N_l][12], 7 counts[T], 8 es[slots] */
 /* Debug knobs (tests / tools only): key 0 = number of interaction layers to run (default 6); key 1 = wait-cycle accounting of the
  * fused conv kernels on (1) / off (0): 148 CTAs x 32 int64 counters (slots 0..7 MMA-issuing warp, 8..15 one fold warp; only filled by a
- * library built with -DB200DOCK_TRACE), read back with b200dock_debug_tap(what = 7). */
+ * library built with -DB200DOCK_TRACE), read back with b200dock_debug_tap(what = 7); key 2 = node update in its warp-per-node
+ * cross-check form (1) instead of the thread-per-(node, irreps block) kernel (0, default; bit-identical). */
 int b200dock_debug_set(B200Handle* h, int key, int value);
 int b200dock_debug_tap(B200Handle* h, int what, int arg, void* host_out, size_t cap_bytes, size_t* n_bytes);
 

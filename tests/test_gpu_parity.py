@@ -459,3 +459,22 @@ def test_bench_batch_trajectory_against_oracle_fixture(sd):
         print(f"kernel {kernel}: 40x20 bench batch vs oracle: final ligand RMSD {per_step[-1]:.2e} A, worst step {max(per_step):.2e} A, "
               f"atom14 {rmsd(a14.cpu(), g['atom14_final']):.2e} A")
         assert max(per_step) <= 1e-3 and rmsd(a14.cpu(), g["atom14_final"]) <= 1e-3
+
+
+def test_node_update_forms_bit_identical(sd):
+    """The thread-per-(node, irreps block) node update reproduces the warp-per-node form's summation order (lane partial sums, xor
+    butterfly, the same FMA contractions): identical bits of the node features after every layer."""
+    b = synth.make_batch(**synth.WORKLOADS["cfgA"], seed=0)
+    c = conditioning(b)
+    eng = make_engine(11, sd)
+    taps = {}
+    for form in (0, 1):
+        eng.debug_set(2, form)
+        for layers in (1, 3, 6):
+            eng.debug_set(0, layers)
+            run_score(eng, b, c)
+            taps[(form, layers)] = (eng.tap(0).copy(), eng.tap(1).copy())
+    eng.debug_set(2, 0); eng.debug_set(0, 6)
+    for layers in (1, 3, 6):
+        for a, r in zip(taps[(0, layers)], taps[(1, layers)]):
+            assert np.array_equal(a, r)

@@ -162,14 +162,21 @@ def cpu_baseline(workload="cfgA", n_poses=4, steps=2, threads=None, seed=0):
 
 def run_reference_arm(args):
     """The reference's CPU path (oracle port; O1 == O2 bit-exactly on the committed fixtures): every timed step is ONE REAL
-    denoising step of the full 40-pose cfg-A batch with all host threads - no extrapolation.  A single-thread figure (what the
+    denoising step of the first P poses of the 40-pose cfg-A batch with all host threads, P = as many as fit a ~200 s budget for the
+    K + W steps (all 40 when they fit), scaled by 40 / P to the 40-pose step.  A single-thread figure (what the
     reference's setup_multi_processes requests, dist_utils.py:265-282) is measured on a bounded sample and reported beside it."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count()
     kw = dict(synth.JOBS[args.workload]); kw.pop("shared_ligand", None); kw["n_complex"] = 1
-    b = synth.make_batch(**kw, seed=0)
     K, W = args.steps, max(args.warmup, 0)
+    # bounded sample: as many poses of the batch per step as fit a ~200 s budget for the K + W steps (the full batch when it fits)
+    cal = dict(kw); cal["n_poses"] = min(4, kw["n_poses"])
+    d0, _, _, _ = oracle_steps(synth.make_batch(**cal, seed=0), 2, threads)
+    per_pose = d0[-1] / cal["n_poses"]
+    budget_s = float(os.environ.get("B200DOCK_REF_BUDGET_S", "200"))
+    kw["n_poses"] = int(max(1, min(kw["n_poses"], budget_s / max((K + W) * per_pose, 1e-9))))
+    b = synth.make_batch(**kw, seed=0)
     dts, _, _, _ = oracle_steps(b, K + W, threads)
     timed = dts[W:]
     ms = float(np.mean(timed)) * 1e3
@@ -180,12 +187,13 @@ def run_reference_arm(args):
         d1, _, _, _ = oracle_steps(synth.make_batch(**kw1, seed=0), 2, 1)
         one = {"value": 1.0 / (d1[-1] * 40.0 / kw1["n_poses"]), "unit": UNIT, "cores": 1,
                "sample": f"{kw1['n_poses']} poses x 1 step after 1 warm-up step, 1 thread, {d1[-1]:.2f} s, scaled to 40 poses"}
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms,
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 / val, "sample_ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{args.workload}: {int(b['num_graphs'])} poses x {int(b['rec_atm_pos'].shape[0]) // int(b['num_graphs'])} pocket atoms x "
-                                   f"{int(b['lig_pos'].shape[0]) // int(b['num_graphs'])} ligand atoms; every timed step is one real denoising step of the whole batch"},
+            "config": {"workload": f"{args.workload}: {int(b['num_graphs'])} of {synth.JOBS[args.workload]['n_poses']} poses x {int(b['rec_atm_pos'].shape[0]) // int(b['num_graphs'])} pocket atoms x "
+                                   f"{int(b['lig_pos'].shape[0]) // int(b['num_graphs'])} ligand atoms; every timed step is one real denoising step of these poses (the first "
+                                   f"poses of the bench batch; as many as fit a {budget_s:.0f} s budget for {K + W} steps), scaled to the 40-pose step"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{K} real steps of the full batch after {W} warm-up steps, oracle/sampler.py (the reference's algorithm on torch CPU "
+                             "sample": f"{K} real steps of {int(b['num_graphs'])} poses after {W} warm-up steps, oracle/sampler.py (the reference's algorithm on torch CPU "
                                        f"kernels; the reference itself cannot be installed: e3nn / torch-scatter / torch-cluster wheels are absent), {threads} threads",
                              "single_thread": one},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}

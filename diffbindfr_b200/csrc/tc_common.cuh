@@ -191,7 +191,8 @@ __device__ __forceinline__ void fold_unit_w12(uint32_t taddr, const float* xp, i
 
 namespace tc {
 // Folds with the channel factors z already in registers (computed while waiting for the accumulator): after the accumulator
-// arrives only tensor-memory loads and packed FMAs remain, so it is held for a shorter time.  Same products in the same order as
+// arrives only tensor-memory loads and packed FMAs remain, and `release` hands it back to the tensor pipe as soon as its last
+// columns are in registers, so it is held for a shorter time.  Same products in the same order as
 // fold_unit_w48 / fold_unit_w12: bit-identical results.
 __device__ __forceinline__ void zfactors_w48(const float* xp, int d1, const float* M, float zs, float* z) {
 #pragma unroll
@@ -213,7 +214,8 @@ __device__ __forceinline__ void zfactors_w12(const float* xp, int d1, const floa
     z[uu * 3] = z0 * zs; z[uu * 3 + 1] = z1 * zs; z[uu * 3 + 2] = z2 * zs;
   }
 }
-__device__ __forceinline__ void fold_z_w48(uint32_t taddr, const float* z, float* o) {
+template <typename Release>
+__device__ __forceinline__ void fold_z_w48(uint32_t taddr, const float* z, float* o, Release release) {
   float va[48], vb[48];
   tmem_ld16(taddr, va); tmem_ld16(taddr + 16, va + 16); tmem_ld16(taddr + 32, va + 32);
 #pragma unroll
@@ -222,6 +224,7 @@ __device__ __forceinline__ void fold_z_w48(uint32_t taddr, const float* z, float
     float* nxt = (c & 1) ? va : vb;
     tmem_wait_ld();
     if (c + 1 < 3) { const uint32_t a = taddr + (c + 1) * 48; tmem_ld16(a, nxt); tmem_ld16(a + 16, nxt + 16); tmem_ld16(a + 32, nxt + 32); }
+    else release();                                    // the whole accumulator is in registers: hand it back before the last FMAs
     const float2 zz = make_float2(z[c], z[c]);
 #pragma unroll
     for (int w = 0; w < 48; w += 2) {
@@ -230,7 +233,8 @@ __device__ __forceinline__ void fold_z_w48(uint32_t taddr, const float* z, float
     }
   }
 }
-__device__ __forceinline__ void fold_z_w12(uint32_t taddr, const float* z, float* o) {
+template <typename Release>
+__device__ __forceinline__ void fold_z_w12(uint32_t taddr, const float* z, float* o, Release release) {
   float va[48], vb[48];
   tmem_ld16(taddr, va); tmem_ld16(taddr + 16, va + 16); tmem_ld16(taddr + 32, va + 32);
 #pragma unroll
@@ -239,6 +243,7 @@ __device__ __forceinline__ void fold_z_w12(uint32_t taddr, const float* z, float
     float* nxt = (c & 1) ? va : vb;
     tmem_wait_ld();
     if (c + 1 < 3) { const uint32_t a = taddr + (c + 1) * 48; tmem_ld16(a, nxt); tmem_ld16(a + 16, nxt + 16); tmem_ld16(a + 32, nxt + 32); }
+    else release();
 #pragma unroll
     for (int u4 = 0; u4 < 4; ++u4) {
       const int uu = c * 4 + u4;

@@ -8,7 +8,7 @@ Mirrors what ``TensorProductModel.__init__`` builds from the shipped config
 The Clebsch-Gordan tensors are generated here (Racah formula + real/complex change of
 basis, the algorithm e3nn 0.5.1 publishes in ``e3nn/o3/_wigner.py``) and handed to the
 CUDA side as sparse tables; the oracle carries its own restatement and the two are
-compared in ``tests/test_spec.py``.
+compared in ``tests/test_oracle.py::test_product_cg_tables_match_oracle``.
 """
 from __future__ import annotations
 

@@ -189,3 +189,33 @@ def test_cuda_error_correction_on_sampler_output(corrector):
     x0, x1 = ligp.double().cpu().numpy(), out["lig_xyz"].double().cpu().numpy()
     for a, c in bonds:
         assert np.abs(np.linalg.norm(x0[:, a] - x0[:, c], axis=-1) - np.linalg.norm(x1[:, a] - x1[:, c], axis=-1)).max() < 1e-3
+
+
+def test_pocket_typing_from_the_atom14_layout_equals_typing_from_pdb_records(gold):
+    """``vina_types.pocket_types_atom14`` (what the device pipeline uses: residue types + atom14 mask + coordinates) gives the same
+    radii / flags as ``receptor_types`` on the PDB records of the same pocket, including the peptide-bond rule for backbone N."""
+    from diffbindfr_b200.constants import RESTYPES
+    from diffbindfr_b200.export import ATOM14_NAMES, RESNAME3
+    pk = gold["G"]["pocket"]
+    three2idx = {RESNAME3[a]: i for i, a in enumerate(RESTYPES)}
+    keys, seen = [], set()
+    for c, r in zip(pk["chains"], pk["resnums"]):
+        if (c, r) not in seen:
+            seen.add((c, r)); keys.append((c, r))
+    nres = len(keys)
+    slot = {k: i for i, k in enumerate(keys)}
+    aatype = np.zeros(nres, dtype=np.int64); mask = np.zeros((nres, 14), dtype=bool); a14 = np.zeros((nres, 14, 3))
+    order = {}
+    for i, (n, res, c, r, x) in enumerate(zip(pk["names"], pk["resnames"], pk["chains"], pk["resnums"], pk["xyz"])):
+        k = slot[(c, r)]
+        aatype[k] = three2idx[res]
+        if n in ATOM14_NAMES[res]:
+            a = ATOM14_NAMES[res].index(n)
+            mask[k, a] = True; a14[k, a] = x; order[(k, a)] = i
+    xyz, R, F = vt.pocket_types_atom14(aatype, mask, a14, [k[0] for k in keys], [k[1] for k in keys])
+    idx = [order[(k, a)] for k in range(nres) for a in range(14) if mask[k, a]]
+    assert len(idx) == len(R) >= 0.99 * len(pk["names"])          # OXT and the like have no atom14 slot
+    assert np.allclose(xyz, np.asarray(pk["xyz"])[idx])
+    assert np.array_equal(R, gold["rR"][idx]) and np.array_equal(F, gold["rF"][idx])
+    n_amide = sum(1 for i in idx if pk["names"][i] == "N" and gold["rF"][i].tolist() == [0, 1, 0])
+    assert n_amide > 20                                            # most backbone N of the pocket are peptide bonded: donor only

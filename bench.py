@@ -36,7 +36,7 @@ UNIT = "steps/s"
 KNAME = {0: "k_conv_tp_simt (exact fp32 SIMT)", 5: "k_conv_fused16 (tcgen05, 3xFP16 split, fused FC1+FC2+fold)",
          6: "k_conv_fused16x2 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, fused FC1+FC2+fold+scatter)",
          11: "k_conv_fused16x2<true> (kernel 6 + a gather / fp16-split / H1-conversion warpgroup working one tile ahead; tcgen05 cta_group::2 CTA pairs, 3xFP16 split, fused scatter)",
-         10: "k_conv_v3 (tcgen05 cta_group::2 CTA pairs, 3xFP16 split, two A buffers in TMEM, 96-column units, fused scatter)"}
+         }
 POSED = ("cfgA", "3dbs", "3dbs_x40")            # single-complex workloads: host-provided starting poses (fixture parity)
 
 
@@ -536,7 +536,7 @@ def main():
     achieved = flops_tp / (tp_ms * 1e-3) / 1e12 if tp_ms > 0 else None
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", {6: "r02_fused16x2_ncu_step.json", 10: "r02_v3_ncu_step.json", 11: "r02_split_ncu_step.json"}[args.conv_kernel])))
+        tj = json.load(open(os.path.join(ROOT, "profiles", {6: "r02_fused16x2_ncu_step.json", 11: "r02_split_ncu_step.json"}[args.conv_kernel])))
         if args.workload == "cfgA":
             traffic = tj["dram_bytes_per_launch"]
     except Exception:

@@ -9,6 +9,6 @@ model = dict(
     type='DiffBindFRB200',
     diffusion_model=dict(
         type='TensorProductModelB200',
-        conv_kernel=11,   # 11: fused tcgen05 FP16x3 on CTA pairs + look-ahead gather warpgroup (fp32-grade, default); 6 / 5: the same without look-ahead / on single CTAs (bit-identical); 10: two-A-buffer experiment; 0: fp32 SIMT
+        conv_kernel=11,   # 11: fused tcgen05 FP16x3 on CTA pairs + look-ahead gather warpgroup (fp32-grade, default); 6 / 5: the same without look-ahead / on single CTAs (bit-identical); 0: fp32 SIMT
     ),
 )

@@ -17,7 +17,6 @@
 #include "tc_common.cuh"
 #include "conv_fused.cuh"
 #include "conv_fused2.cuh"
-#include "conv_v3.cuh"
 #include "heads.cuh"
 #include "pose.cuh"
 #include "mdn.cuh"
@@ -56,8 +55,8 @@ struct ConvW {                  // views into the device weight blob
 
 // conv kernels: 0 exact fp32 SIMT (192-column units), 5 fused tcgen05 single CTA, 6 fused tcgen05 CTA pairs + fused scatter (144),
 // 10 the pair kernel re-pipelined over two A buffers with 96-column units (no tile-transition bubble)
-inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6 || k == 10 || k == 11; }
-inline int variant_of_kernel(int k) { return k == 0 ? 0 : (k == 10 ? 2 : 1); }
+inline bool kernel_known(int k) { return k == 0 || k == 5 || k == 6 || k == 11; }
+inline int variant_of_kernel(int k) { return k == 0 ? 0 : 1; }
 inline bool kernel_keeps_msg(int k) { return k == 0 || k == 5; }
 
 }  // namespace
@@ -225,8 +224,7 @@ int launch_tp(B200Handle* h, const ConvLaunch& L, const Fused16Extra& F, cudaStr
   if (h->profiling) { e0 = get_event(h); e1 = get_event(h); cudaEventRecord(e0, st); }
   int rc = B200_OK;
   const int k = h->cfg.conv_kernel;
-  if (k == 10) rc = launch_conv_v3(L, F, h->tp_grid, st);
-  else if (k == 6) {
+  if (k == 6) {
     static const int dbg = getenv("B200DOCK_DBG") ? atoi(getenv("B200DOCK_DBG")) : 0;   // honoured by the -DB200DOCK_TRACE build only
     ConvLaunch L2 = L; L2.dbg = dbg;
     rc = launch_conv_fused16x2(L2, F, h->tp_grid, st);
@@ -541,7 +539,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   *out = h;
   h->device = device;
   h->cfg = *cfg;
-  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs, 10 re-pipelined pair kernel, 11 pair kernel with a gather/convert warpgroup)");
+  if (!kernel_known(cfg->conv_kernel)) FAIL(B200_ERR_INVALID, "unknown conv_kernel (0 exact fp32 SIMT, 5 fused tcgen05, 6 fused tcgen05 on CTA pairs, 11 pair kernel with a gather/convert warpgroup)");
   h->variant = variant_of_kernel(cfg->conv_kernel);
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -595,7 +593,7 @@ int b200dock_create(const B200Config* cfg, int device, B200Handle** out) {
   if ((rc = upload(h, cfg->tor_cg_val, (size_t)cfg->tor_cg_off[3], &h->d_tor_cg_val))) return rc;
   CK(cudaFuncSetAttribute(k_conv_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRO_SMEM));
   CK(cudaFuncSetAttribute(k_conv_tp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
-  if (tc_init() || conv_fused_init() || conv_fused2_init() || conv_v3_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
+  if (tc_init() || conv_fused_init() || conv_fused2_init()) FAIL(B200_ERR_CUDA, "tcgen05 conv kernel attribute setup failed");
   h->cfg.atom14_group = nullptr; h->cfg.tor_cg_ijk = nullptr; h->cfg.tor_cg_val = nullptr;
   return B200_OK;
 }

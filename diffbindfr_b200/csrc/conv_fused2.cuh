@@ -150,7 +150,7 @@ k_conv_fused16x2(ConvLaunch L, const __grid_constant__ FusedMaps maps) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-  if (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // registers to where they are needed: 56 / 232 / 208 per thread (sum < 512, see conv_v3.cuh)
+  if (SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");   // registers to where they are needed: 56 / 232 / 208 per thread (the sum stays below the 512 three warpgroups may hold: at exactly 512 the last setmaxnreg.inc never returned)
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs: own 72 rows)
     if (lane == 0)

@@ -124,9 +124,7 @@ class Engine:
     """One handle = one device.  ``conv_kernel``: 0 exact fp32 SIMT contraction (cross-check), 5 fused tcgen05 kernel with FP16
     hi/lo error-compensated MMAs and per-row scaling (fp32-grade; per-edge message rows + a separate segmented scatter),
     6 the same on CTA pairs (tcgen05 cta_group::2) with the scatter fused into the epilogue (bit-identical to 5),
-    11 kernel 6 plus a warpgroup that gathers / converts the next tile's edge input one tile ahead (default; bit-identical),
-    10 the pair kernel re-pipelined over two A buffers in tensor memory (96-column units, separate gather / fold warpgroups:
-    no tile-transition bubble; bit-identical to 5 and 6)."""
+    11 kernel 6 plus a warpgroup that gathers / converts the next tile's edge input one tile ahead (default; bit-identical)."""
 
     def __init__(self, device: int = 0, conv_kernel: int = 11):
         if not torch.cuda.is_available():

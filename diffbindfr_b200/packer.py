@@ -122,13 +122,10 @@ class Plans:
                 off += m * (2 * l + 1)
                 irr += m
             ijk = np.ascontiguousarray(np.concatenate(ijk_all)); val = np.ascontiguousarray(np.concatenate(val_all))
-            ch = np.asarray(chunks_of(tp, {5: 144, 6: 144, 10: 96, 11: 144}.get(conv_kernel, CHUNK_COLS)), dtype=np.int32)
+            ch = np.asarray(chunks_of(tp, {5: 144, 6: 144, 11: 144}.get(conv_kernel, CHUNK_COLS)), dtype=np.int32)
             cc, cn, cpth = (np.ascontiguousarray(ch[:, k]) for k in range(3))
             if pid != 5:   # plan 5 = centre conv (own kernel)
-                assert conv_kernel not in (5, 6, 11) or (cn == 144).all(), "kernels 5 / 6 fold whole 144-column units"
-                if conv_kernel == 10:   # 96-column units; 12x12 path blocks (144 columns) end with a 48-column unit of a 12-wide path
-                    wd = np.asarray([tp.paths[i].mulo for i in cpth])
-                    assert (((cn == 96) | ((cn == 48) & (wd == 12)))).all(), "kernel 10 folds 96-column units (48 for the tail of 12x12 blocks)"
+                assert conv_kernel not in (5, 6, 11) or (cn == 144).all(), "kernels 5 / 6 / 11 fold whole 144-column units"
             self.keep += [ijk, val, cc, cn, cpth]
             cp.n_cg = len(ijk)
             cp.cg_ijk = ijk.ctypes.data_as(C.POINTER(C.c_int32)); cp.cg_val = val.ctypes.data_as(C.POINTER(C.c_float))

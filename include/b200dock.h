@@ -100,8 +100,7 @@ typedef struct {
   B200ConvPlan plans[B200_N_PLANS];
   int32_t conv_kernel;      /* 0 exact fp32 SIMT (cross-check), 5 fused tcgen05 conv with FP16 hi/lo MMAs + per-row scaling
                                (fp32-grade; message rows + separate scatter), 6 the same on CTA pairs (cta_group::2) with the
-                               scatter fused into the epilogue (bit-identical to 5), 10 the pair kernel over two A buffers with 96-column
-                               units (experiment; bit-identical), 11 kernel 6 plus a warpgroup that gathers / converts the next tile's
+                               scatter fused into the epilogue (bit-identical to 5), 11 kernel 6 plus a warpgroup that gathers / converts the next tile's
                                edge input one tile ahead and converts H1 (default of the Python layer; bit-identical) */
   int32_t reserved[7];
   const int32_t* atom14_group;  /* [21][14] restype_atom14_to_rigid_group (protein_constants.py:1177-1199) */

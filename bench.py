@@ -557,7 +557,7 @@ def main():
                              "steps_per_s": sustained["value"], "clocks": sustained["clocks"],
                              "note": f"{sustained['reps']} back-to-back repetitions of the K-step call (inputs re-uploaded between repetitions, outside the events)"}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # the CPU baseline is a rank-0, N = 1 figure
         cpu = cpu_baseline(args.workload, n_poses=min(args.cpu_baseline_poses, dict(synth.JOBS[args.workload])["n_poses"]), steps=2)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "fp16x3" if args.conv_kernel else "f32", "data": "synthetic",

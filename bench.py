@@ -265,6 +265,8 @@ def main():
     ap.add_argument("--conv-kernel", type=int, default=int(os.environ.get("B200DOCK_CONV_KERNEL", "11")))
     ap.add_argument("--batch-size", type=int, default=320, help="samples per device batch of the multi-complex workloads")
     ap.add_argument("--complexes", type=int, default=0, help="override the number of complexes of a multi-complex workload")
+    ap.add_argument("--balance", action="store_true", help="multi-complex jobs: deal whole complexes to ranks by estimated cost (LPT) instead of the "
+                    "reference's static round-robin")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mdn", action="store_true", help="skip the MDN rescoring stage")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained loop")
@@ -458,7 +460,7 @@ def main():
         barrier()
         clocks = ClockSampler(local) if rank == 0 else None
         t0 = time.perf_counter()
-        rec_j, max_nl_j = dk.dock(complexes, P, steps_k, batch_size=args.batch_size, unpack=False)
+        rec_j, max_nl_j = dk.dock(complexes, P, steps_k, batch_size=args.batch_size, unpack=False, balance=args.balance)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         got = shard.unpack_records(rec_j.cpu(), max_nl_j)
@@ -513,7 +515,8 @@ def main():
                               f"batches of {args.batch_size}, one all_gather of coordinate+score records",
                   "complexes": len(complexes), "poses": P, "batch_size": args.batch_size, "batches": int(allsum(dk.stats["batches"])),
                   "edges_summed_over_batches": counts, "conv_kernel": args.conv_kernel, "random_init_weights": True,
-                  "parallelism": f"sample-sharded x{world} (strong scaling of a fixed job)",
+                  "parallelism": f"sample-sharded x{world} (strong scaling of a fixed job; " + ("whole complexes dealt by estimated cost, longest first" if args.balance
+                                 else "the reference's static round-robin in pose-major order") + ")",
                   "rank_device_ms": rank_ms, "imbalance_max_over_mean": (max(rank_ms) / (sum(rank_ms) / len(rank_ms))) if sum(rank_ms) else None,
                   "limiter": "slowest rank's device time (round-robin deals ragged complexes unevenly); the final all_gather moves "
                              f"{n_samples} fixed-stride records once",

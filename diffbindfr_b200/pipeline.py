@@ -108,12 +108,12 @@ class Docker:
 
     # ------------------------------------------------------------------ whole job, sharded over the ranks
     def dock(self, complexes, n_poses: int, steps, batch_size: int = 320, seed: int = 0, tr_sigma_max: float = 10.0,
-             noise_seed: int = 1, group=None, unpack: bool = True):
+             noise_seed: int = 1, group=None, unpack: bool = True, balance: bool = False):
         """All ``len(complexes) * n_poses`` samples; every rank ends with {sample id: (lig, atom14[, score])} for the whole job
         (``unpack=False``: the gathered record tensor and ``max_nl``, see ``shard.run_sharded``)."""
         samples = job_samples(complexes, n_poses)
         run = lambda chunk: self.dock_batch(complexes, chunk, steps, seed, tr_sigma_max, noise_seed)
-        return shard.run_sharded(samples, run, batch_size, group=group, device=self.device, unpack=unpack)
+        return shard.run_sharded(samples, run, batch_size, group=group, device=self.device, unpack=unpack, balance=balance)
 
 
 def mdn_inputs_from_poses_torch(lig_pos: torch.Tensor, atom14: torch.Tensor, batch: Dict[str, object], static: Sequence[Dict[str, torch.Tensor]],

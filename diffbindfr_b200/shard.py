@@ -19,6 +19,30 @@ def shard_indices(n_samples: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_samples, world))
 
 
+def sample_cost(n_res: int, n_lig: int) -> float:
+    """Rough relative cost of one denoising step of a sample = its conv edges: pocket atom graph (~8.3 atoms per residue, ~13
+    neighbours within 4 A), the two cross graphs (every ligand atom against CA and CB of every residue) and the ligand graph."""
+    return 108.0 * n_res + 4.0 * n_res * n_lig + 20.0 * n_lig
+
+
+def balanced_indices(costs: Sequence[float], groups: Sequence[int], rank: int, world: int) -> List[int]:
+    """Cost-aware alternative to the reference's static round-robin: whole groups (= complexes, so that the poses of a complex
+    stay together and its pocket is replicated on one device) are dealt longest-processing-time first to the least loaded rank.
+    Deterministic and identical on every rank; ties go to the lower rank / lower group id."""
+    by_group: Dict[int, List[int]] = {}
+    for i, g in enumerate(groups):
+        by_group.setdefault(int(g), []).append(i)
+    gcost = {g: sum(float(costs[i]) for i in idx) for g, idx in by_group.items()}
+    load = [0.0] * world
+    mine: List[int] = []
+    for g in sorted(by_group, key=lambda g: (-gcost[g], g)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        load[r] += gcost[g]
+        if r == rank:
+            mine.extend(by_group[g])
+    return sorted(mine)
+
+
 def batches(indices: Sequence[int], batch_size: int) -> List[List[int]]:
     return [list(indices[i:i + batch_size]) for i in range(0, len(indices), batch_size)]
 
@@ -103,20 +127,29 @@ def gather_poses(ids, ligs, a14s, n_samples: int, max_nl: int, max_nr: int, grou
 
 
 def run_sharded(samples: Sequence[dict], run_batch: Callable[[List[dict]], object], batch_size: int, collate=None, group=None, device=None,
-                unpack: bool = True):
+                unpack: bool = True, balance: bool = False):
     """Deal ``samples`` to ranks, run ``run_batch`` on local batches, gather all final poses.
     ``run_batch(list_of_samples)`` returns either [(lig (n_l,3), atom14 (n_r,14,3))] per sample - 3-tuples with the sample's MDN
     score appended when the scorer ran on the rank that sampled the pose (the score travels in the same record) - or one
     ``BatchResult`` for the whole batch (packed on the device without per-sample Python).  A sample record needs ``lig_pos`` and
     ``sequence`` (sizes) and, optionally, ``id`` (default: its index).  ``unpack=False`` returns the gathered record tensor
-    ``(world, n_slots, stride)`` and ``max_nl`` instead of the per-sample dict (``unpack_records`` turns it into one later)."""
+    ``(world, n_slots, stride)`` and ``max_nl`` instead of the per-sample dict (``unpack_records`` turns it into one later).
+    ``balance=True`` replaces the reference's round-robin by ``balanced_indices`` (samples need a ``complex`` key)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = len(samples)
-    mine = shard_indices(n, rank, world)
+    if balance and world > 1:
+        costs = [sample_cost(int(s_["sequence"].shape[0]), int(s_["lig_pos"].shape[0])) for s_ in samples]
+        groups = [int(s_["complex"]) for s_ in samples]
+        per_rank = [balanced_indices(costs, groups, r, world) for r in range(world)]
+        mine = per_rank[rank]
+        n_slots_bal = max(len(x) for x in per_rank)
+    else:
+        mine = shard_indices(n, rank, world)
+        n_slots_bal = None
     max_nl = max(int(s["lig_pos"].shape[0]) for s in samples)
     max_nr = max(int(s["sequence"].shape[0]) for s in samples)
-    n_slots = (n + world - 1) // world
+    n_slots = n_slots_bal if n_slots_bal is not None else (n + world - 1) // world
     rec = None
     ids, ligs, a14s, scores = [], [], [], []
     slot = 0

@@ -190,6 +190,12 @@ def _worker(rank, world, port, q):
     ok &= sorted(got) == [0] and len(got[0]) == 3 and abs(got[0][2] - 1.5) < 1e-6
     got = shard.run_sharded(samples[:1], run_batch, batch_size=2)            # and without scores: 2-tuples everywhere
     ok &= len(got[0]) == 2
+    # cost-balanced dealing of whole complexes (3 complexes x poses, uneven counts per rank): same records for everybody
+    grouped = [dict(s, complex=i % 3) for i, s in enumerate(samples)]
+    got = shard.run_sharded(grouped, run_batch, batch_size=2, balance=True)
+    ok &= sorted(got) == list(range(7))
+    for i, s in enumerate(samples):
+        ok &= torch.allclose(got[i][0], torch.from_numpy(s["lig_pos"]) * 2 + 1)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
@@ -203,6 +209,26 @@ def test_two_rank_gloo_shard_and_gather():
     res = [q.get(timeout=120) for _ in ps]
     [p.join(timeout=60) for p in ps]
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_balanced_dealing_keeps_complexes_together_and_evens_the_load():
+    """``shard.balanced_indices``: a partition of the sample list, every complex on ONE rank, identical on all ranks, and on a
+    ragged PoseBusters-shape set a smaller max / mean load than the reference's round-robin of whole complexes."""
+    rng = np.random.default_rng(1)
+    n_cx, n_pose, world = 64, 5, 8
+    nres, nlig = rng.integers(30, 111, n_cx), rng.integers(15, 51, n_cx)
+    groups = [c for _ in range(n_pose) for c in range(n_cx)]                  # pose-major sample order
+    costs = [shard.sample_cost(int(nres[c]), int(nlig[c])) for c in groups]
+    parts = [shard.balanced_indices(costs, groups, r, world) for r in range(world)]
+    assert sorted(i for p in parts for i in p) == list(range(n_cx * n_pose))
+    owner = {}
+    for r, p in enumerate(parts):
+        for i in p:
+            assert owner.setdefault(groups[i], r) == r
+    load = lambda idx: sum(costs[i] for i in idx)
+    bal = max(load(p) for p in parts) / (sum(costs) / world)
+    rr = max(load(shard.shard_indices(len(costs), r, world)) for r in range(world)) / (sum(costs) / world)
+    assert bal < 1.02 < rr
 
 
 def test_karmadock_plugin_state_dict_contract():

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import batch as batch_mod
+from . import batch as batch_mod, philox
 from . import mdn_features, shard, synth
 from .engine import Engine
 from .mdn import MDNScorer
@@ -32,6 +32,37 @@ def job_samples(complexes: Sequence[Dict[str, np.ndarray]], n_poses: int) -> Lis
     n = len(complexes)
     return [dict(id=k * n + p, complex=p, pose=k, lig_pos=complexes[p]["lig_pos"], sequence=complexes[p]["sequence"])
             for k in range(n_poses) for p in range(n)]
+
+
+def sample_noise(complexes, samples: Sequence[Dict[str, object]], n_steps: int, noise_seed: int, device=None) -> torch.Tensor:
+    """SDE noise of a batch, (n_steps, 6 B + n_tor + n_sc) in the sampler's layout [tr | rot | tor | sc] (scFlex.py:167-183), generated
+    on ``device``.  Every sample owns a counter-based stream keyed by (noise_seed, sample id) - Philox, like the device pose
+    initialisation - so a sample's noise, and with the deterministic kernels its whole trajectory, does not depend on which batch
+    or rank it lands in (results on identical seeds are independent of the sharding).  The last step carries no
+    noise (no_final_step_noise, diffbindfr_ts.py:144-163)."""
+    B = len(samples)
+    cnt = {}
+    for s in samples:
+        c = int(s["complex"])
+        if c not in cnt:
+            cnt[c] = (int(np.asarray(complexes[c]["tor_edge_mask"]).sum()), int(np.asarray(complexes[c]["sc_torsion_edge_mask"]).sum()))
+    nt = torch.tensor([cnt[int(s["complex"])][0] for s in samples], dtype=torch.int64, device=device)
+    ns = torch.tensor([cnt[int(s["complex"])][1] for s in samples], dtype=torch.int64, device=device)
+    ids = torch.tensor([int(s["id"]) for s in samples], dtype=torch.int64, device=device)
+    n_tor, n_sc = int(nt.sum()), int(ns.sum())
+    wmax = int((6 + nt + ns).max()) if B else 0
+    z = philox.normals(int(noise_seed), ids, n_steps, wmax).permute(1, 0, 2)       # (steps, B, wmax): sample g uses its first 6 + nt + ns
+    out = torch.zeros(n_steps, 6 * B + n_tor + n_sc, dtype=torch.float32, device=device)
+    out[:, :3 * B] = z[:, :, 0:3].reshape(n_steps, 3 * B)
+    out[:, 3 * B:6 * B] = z[:, :, 3:6].reshape(n_steps, 3 * B)
+    col = torch.arange(wmax, device=device)[None, :]
+    m_t = (col >= 6) & (col < 6 + nt[:, None])                                     # (B, wmax) masks; row-major order = graph order
+    m_s = (col >= 6 + nt[:, None]) & (col < (6 + nt + ns)[:, None])
+    out[:, 6 * B:6 * B + n_tor] = z[:, m_t]
+    out[:, 6 * B + n_tor:] = z[:, m_s]
+    if n_steps:
+        out[-1] = 0.0
+    return out
 
 
 class Docker:
@@ -79,10 +110,8 @@ class Docker:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         cb = self.eng.expand(base, src, ids, seed=seed, tr_sigma_max=tr_sigma_max)
-        g = torch.Generator().manual_seed(noise_seed * 1000003 + ids[0])
-        noise = torch.randn(len(steps), 6 * cb.B + cb.n_tor + cb.n_sc, generator=g)
-        if len(steps):
-            noise[-1] = 0.0                                  # no_final_step_noise (diffbindfr_ts.py:144-163)
+        noise = sample_noise(complexes, samples, len(steps), noise_seed, self.device)
+        assert noise.shape[1] == 6 * cb.B + cb.n_tor + cb.n_sc
         lig, a14 = self.eng.sample_expanded(cb, steps, noise)
         launches = self.eng.launch_count()
         scores = None

@@ -123,15 +123,23 @@ class SdfTemplate:
         t.n_atoms = na
         return t
 
-    def render(self, pos: np.ndarray) -> List[str]:
-        """``pos`` (P, n_atoms, 3) or (n_atoms, 3) -> one SDF record per pose."""
+    def render(self, pos: np.ndarray, tags: Optional[Dict[str, Sequence[float]]] = None) -> List[str]:
+        """``pos`` (P, n_atoms, 3) or (n_atoms, 3) -> one SDF record per pose.  ``tags``: SD data items, one value per pose
+        (e.g. ``minimizedAffinity``, the tag smina writes and ``get_smina_score`` reads back, druglib/ops/smina/__init__.py:16-22)."""
         x = np.asarray(pos, dtype=np.float64)
         if x.ndim == 2:
             x = x[None]
         assert x.shape[1] == self.n_atoms
         txt = _fmt_cols(x, 10, 4)
         lines = np.char.add(np.char.add(np.char.add(txt[..., 0], txt[..., 1]), txt[..., 2]), self.atom_tail[None])
-        return [self.header + "".join(lines[p].tolist()) + self.footer for p in range(x.shape[0])]
+        out = []
+        for p in range(x.shape[0]):
+            foot = self.footer
+            if tags:
+                data = "".join(f"> <{k}>\n{float(v[p]):.5f}\n\n" for k, v in tags.items())
+                foot = foot.replace("$$$$\n", data + "$$$$\n")
+            out.append(self.header + "".join(lines[p].tolist()) + foot)
+        return out
 
 
 def export_poses(export_dir: str, complex_name: str, lig_template: SdfTemplate, prot_template: PdbTemplate, lig_poses: np.ndarray,
@@ -160,6 +168,41 @@ def export_poses(export_dir: str, complex_name: str, lig_template: SdfTemplate, 
             f.write(pdb[k])
         out.append(dict(sample_id=name, docked_lig=lp, protein_pdb=pp))
     return out
+
+
+EC_TAG = "_ec"          # DiffBindFR/common: the error-corrected ligand is written next to lig_final.sdf as lig_final_ec.sdf
+
+
+def export_corrected(export_dir: str, complex_name: str, lig_template: SdfTemplate, lig_poses: np.ndarray, affinities: Sequence[float],
+                     pocket_center: Optional[np.ndarray] = None, sample_names: Optional[Sequence[str]] = None,
+                     rmsd_to_start: Optional[Sequence[float]] = None) -> List[str]:
+    """Error-corrected poses of one complex as ``<export_dir>/<complex>/<sample>/lig_final_ec.sdf`` with the SD tags smina writes
+    (``minimizedAffinity``, ``minimizedRMSD``): the files ``error_corrector`` leaves behind and later stages read
+    (DiffBindFR/common/engines.py:304-322, druglib/ops/smina/__init__.py:16-22,113-146).  Returns the paths."""
+    lig = np.asarray(lig_poses, dtype=np.float64)
+    if pocket_center is not None:
+        lig = lig + np.asarray(pocket_center, dtype=np.float64).reshape(1, 1, 3)
+    tags = {"minimizedAffinity": list(affinities)}
+    if rmsd_to_start is not None:
+        tags["minimizedRMSD"] = list(rmsd_to_start)
+    sdf = lig_template.render(lig, tags)
+    paths = []
+    for k in range(lig.shape[0]):
+        name = sample_names[k] if sample_names is not None else f"sample_{k + 1}"
+        d = os.path.join(export_dir, complex_name, name)
+        os.makedirs(d, exist_ok=True)
+        p = os.path.join(d, f"lig_final{EC_TAG}.sdf")
+        with open(p, "w") as f:
+            f.write(sdf[k])
+        paths.append(p)
+    return paths
+
+
+def read_sd_tag(path: str, tag: str) -> float:
+    """What ``get_smina_score`` does with RDKit: the first record's SD data item as a float."""
+    lines = open(path).read().splitlines()
+    i = lines.index(f"> <{tag}>")
+    return float(lines[i + 1])
 
 
 def parse_pdb_coords(text: str) -> np.ndarray:

@@ -3,6 +3,7 @@ import os
 import time
 
 import numpy as np
+import pytest
 
 from diffbindfr_b200 import export, synth
 
@@ -68,3 +69,16 @@ def test_export_throughput_40_poses():
     a, b = pt.render(a14), st.render(lig)
     dt = time.perf_counter() - t0
     assert len(a) == 40 and len(b) == 40 and dt < 2.0, dt
+
+
+def test_error_corrected_export_carries_the_smina_tags(tmp_path):
+    """``lig_final_ec.sdf`` with ``minimizedAffinity`` / ``minimizedRMSD`` SD items, the file ``error_corrector`` leaves per pose."""
+    from diffbindfr_b200 import export
+    t = export.SdfTemplate(["C", "N", "O"], np.array([[0, 1], [1, 2]]), [1, 2])
+    poses = np.arange(18, dtype=np.float64).reshape(2, 3, 3) / 7.0
+    paths = export.export_corrected(str(tmp_path), "cx", t, poses, [-9.43802, 1.5], pocket_center=np.array([1.0, 2.0, 3.0]), rmsd_to_start=[0.4, 0.1])
+    assert [p.split("/")[-2:] for p in paths] == [["sample_1", "lig_final_ec.sdf"], ["sample_2", "lig_final_ec.sdf"]]
+    assert export.read_sd_tag(paths[0], "minimizedAffinity") == pytest.approx(-9.43802) and export.read_sd_tag(paths[1], "minimizedRMSD") == pytest.approx(0.1)
+    txt = open(paths[1]).read()
+    assert txt.rstrip().endswith("$$$$") and txt.count("M  END") == 1
+    assert np.allclose(export.parse_sdf_coords(txt), poses[1] + np.array([1.0, 2.0, 3.0]), atol=1e-4)

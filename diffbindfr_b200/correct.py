@@ -22,12 +22,13 @@ import torch
 class LigandTopology:
     """Torsion tree of a ligand from its heavy-atom bonds, in the layout ``b200dock_vina`` takes.
 
-    Rotatable bond = single, acyclic, both atoms with >= 2 heavy neighbours (OpenBabel ``IsRotor``, what the reference's binary uses
-    to build its tree); every torsion moves the side that does not contain ``root``; torsions are ordered parents first.  The
+    Rotatable bond = single, acyclic, both atoms with >= 2 heavy neighbours and - when ``elements`` are given - not an
+    amide C-N (what the reference's binary keeps in its tree; pinned on the reference's example ligands); every torsion moves the side that does not contain ``root``; torsions are ordered parents first.  The
     intramolecular pair list follows AutoDock Vina 1.1.2: pairs more than 3 bonds apart whose distance can change, where a rigid
     piece extended by the far axis atoms of its torsions counts as fixed."""
 
-    def __init__(self, n_atoms: int, bonds: Sequence[Tuple[int, int]], orders: Optional[Sequence[int]] = None, root: int = 0):
+    def __init__(self, n_atoms: int, bonds: Sequence[Tuple[int, int]], orders: Optional[Sequence[int]] = None, root: int = 0,
+                 elements: Optional[Sequence[str]] = None, n_h: Optional[Sequence[int]] = None):
         n = int(n_atoms)
         bonds = [(int(a), int(b)) for a, b in bonds]
         orders = [int(o) for o in orders] if orders is not None else [1] * len(bonds)
@@ -37,9 +38,21 @@ class LigandTopology:
         comp = self._reach(adj, root, None)
         if len(comp) != n:
             raise ValueError("ligand bond graph is not connected")
+        order_of = {}
+        for (a, b), o in zip(bonds, orders):
+            order_of[(a, b)] = order_of[(b, a)] = o
+
+        def amide(c, n_):                     # C(=O)-N single bond to a nitrogen with three connections (OpenBabel's IsAmide)
+            if elements is None or elements[c] != "C" or elements[n_] != "N":
+                return False
+            conn = len(adj[n_]) + (int(n_h[n_]) if n_h is not None else max(3 - len(adj[n_]), 0))
+            return conn == 3 and any(elements[w] == "O" and order_of[(c, w)] == 2 for w in adj[c])
+
         tors = []
         for (a, b), o in zip(bonds, orders):
             if o != 1 or len(adj[a]) < 2 or len(adj[b]) < 2:
+                continue
+            if amide(a, b) or amide(b, a):
                 continue
             far = self._reach(adj, b, (a, b))
             if a in far:

@@ -4,12 +4,16 @@
 The reference delegates typing to its bundled ``smina.static`` (``druglib/ops/smina/__init__.py:113-146``), i.e. to OpenBabel's
 perception after adding polar hydrogens.  The residue table ``vina_types_table.json`` was MEASURED from that binary for the 20
 standard residues arriving as hydrogen-free PDB records (``tools/smina_probe_types.py``: methane / formaldehyde / zinc probes,
-exact least-squares recovery of the flags).  Two context rules complete it: a backbone N that is peptide-bonded to the previous
+exact least-squares recovery of the flags; PRO CD corrected to non-hydrophobic after the ring closure N-CD showed up in real
+geometry).  Two context rules complete it: a backbone N that is peptide-bonded to the previous
 residue is an amide N (donor unless proline, never an acceptor); everything unknown is typed by element.  Ligands are typed by
 rule from elements, bonds and hydrogen counts: carbon is hydrophobic unless bonded to a heteroatom, N / O are donors when they carry
 hydrogen, O is always an acceptor, N is an acceptor unless it has four connections or three connections in a conjugated (sp2)
-environment (OpenBabel's ``IsHbondAcceptor``), halogens are hydrophobic.  On the reference's example complex (3dbs pocket +
-crystal ligand) this reproduces all five term sums of ``smina --score_only`` to the printed 5 decimals (``tests/test_vina.py``).
+environment (OpenBabel's ``IsHbondAcceptor``), halogens are hydrophobic.  On the reference's example pocket (3dbs) the LIGAND rules reproduce all five term sums of ``smina --score_only`` to the printed
+5 decimals for the crystal ligand and the reference's 15 example ligands; the POCKET rules agree with a per-atom measurement of the
+binary on 646 of 660 atoms - the exceptions are geometry dependent in OpenBabel (which carboxylate oxygen of ASP / GLU carries the
+acid hydrogen, the guanidinium double bond of ARG, histidine tautomers) and can be overridden by passing measured flags
+(``tests/test_vina.py``).
 """
 from __future__ import annotations
 

@@ -85,11 +85,13 @@ def affinity(inter_energy: float, n_rot: float) -> float:
 
 # ---------------------------------------------------------------------------------------------- ligand topology
 class LigandTopology:
-    """Torsion tree of a ligand given heavy-atom bonds: rotatable bonds (single, acyclic, both ends with >= 2 heavy neighbours -
-    OpenBabel's ``IsRotor`` as the binary uses it), the atoms each torsion moves (the side away from the root atom), and the
+    """Torsion tree of a ligand given heavy-atom bonds: rotatable bonds (single, acyclic, both ends with >= 2 heavy neighbours,
+    not an amide C-N - what the binary's OpenBabel-based tree builder keeps; pinned on the 15 example ligands of the
+    reference: rotor counts and intramolecular energies), the atoms each torsion moves (the side away from the root atom), and the
     intramolecular pair list of Vina 1.1.2 (``model::initialize_pairs``): pairs whose distance can change, more than 3 bonds apart."""
 
-    def __init__(self, n_atoms: int, bonds: Sequence[Tuple[int, int]], orders: Optional[Sequence[int]] = None, root: int = 0):
+    def __init__(self, n_atoms: int, bonds: Sequence[Tuple[int, int]], orders: Optional[Sequence[int]] = None, root: int = 0,
+                 elements: Optional[Sequence[str]] = None, n_h: Optional[Sequence[int]] = None):
         self.n = n_atoms
         bonds = [(int(a), int(b)) for a, b in bonds]
         orders = list(orders) if orders is not None else [1] * len(bonds)
@@ -109,9 +111,21 @@ class LigandTopology:
                     seen.add(w); st.append(w)
             return seen
 
+        order_of = {}
+        for (a, b), o in zip(bonds, orders):
+            order_of[(a, b)] = order_of[(b, a)] = o
+
+        def amide(c, n_):                     # OpenBabel OBBond::IsAmide: C(=O)-N single bond to a nitrogen with three connections
+            if elements is None or elements[c] != "C" or elements[n_] != "N":
+                return False
+            conn = len(adj[n_]) + (int(n_h[n_]) if n_h is not None else max(3 - len(adj[n_]), 0))
+            return conn == 3 and any(elements[w] == "O" and order_of[(c, w)] == 2 for w in adj[c])
+
         tors = []
         for (a, b), o in zip(bonds, orders):
             if o != 1 or len(adj[a]) < 2 or len(adj[b]) < 2:
+                continue
+            if amide(a, b) or amide(b, a):     # amide bonds do not rotate in the binary's tree
                 continue
             sb = side(a, b)
             if a in sb:                       # ring bond

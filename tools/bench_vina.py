@@ -13,7 +13,7 @@ pk, lg = G["pocket"], G["ligand"]
 rec = np.asarray(pk["xyz"])
 rT = vt.receptor_types(pk["names"], pk["resnames"], pk["chains"], pk["resnums"], rec)
 lT = vt.ligand_types(lg["elements"], lg["bonds"], lg["orders"], lg["n_h"])
-topo = correct.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"])
+topo = correct.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"], elements=lg["elements"], n_h=lg["n_h"])
 ec = correct.ErrorCorrector(Engine(0))
 X = np.stack([np.asarray(p["xyz"]) for p in G["poses"]])
 out = {}
@@ -22,7 +22,7 @@ for P in (6, 40, 320):
     ec.correct(x, rec, lT, rT, topo); torch.cuda.synchronize()
     t = time.perf_counter(); o = ec.correct(x, rec, lT, rT, topo); aff = o["affinity"].cpu(); dt = time.perf_counter() - t
     out[f"poses_{P}"] = {"ms": dt * 1e3, "poses_per_s": P / dt, "mean_evals": float(o["evals"].float().mean())}
-otopo = ov.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"])
+otopo = ov.LigandTopology(len(lg["elements"]), lg["bonds"], lg["orders"], elements=lg["elements"], n_h=lg["n_h"])
 S = ov.VinaSystem(lT[0], lT[1], otopo, rec, rT[0], rT[1])
 t = time.perf_counter(); m = ov.minimize(S, X[0]); cpu = time.perf_counter() - t
 print(json.dumps({"stage": "error correction (smina --minimize replacement), 3dbs example: 35 ligand atoms, 660 pocket atoms, 5 rotors", "device": out,

@@ -245,3 +245,32 @@ def test_pocket_typing_from_the_atom14_layout_equals_typing_from_pdb_records(gol
     assert np.array_equal(R, gold["rR"][idx]) and np.array_equal(F, gold["rF_rule"][idx])
     n_amide = sum(1 for i in idx if pk["names"][i] == "N" and gold["rF"][i].tolist() == [0, 1, 0])
     assert n_amide > 20                                            # most backbone N of the pocket are peptide bonded: donor only
+
+
+def test_oracle_invariances_and_internal_coordinates(gold):
+    """Properties the domain offers: rigid motions of the whole complex leave every energy unchanged; a ligand-only rigid motion leaves
+    the intramolecular energy unchanged; increments (rigid + torsions) preserve bond lengths and all distances inside a rigid piece;
+    torsion increments on different branches commute."""
+    S, topo = gold["sys64"], gold["topo"]
+    x = gold["poses64"][3]
+    rng = np.random.default_rng(0)
+    Rm = ov._rotvec(rng.normal(size=3)); t = rng.normal(size=3) * 5
+    S2 = ov.VinaSystem(S.lig_R, S.lig_flags, topo, S.rec_xyz @ Rm.T + t, S.rec_R, S.rec_flags)
+    assert abs(S2.inter(x @ Rm.T + t) - S.inter(x)) < 1e-9 and abs(S2.intra(x @ Rm.T + t) - S.intra(x)) < 1e-10
+    step = np.concatenate([rng.normal(size=3), rng.normal(size=3) * 0.5, np.zeros(topo.n_rot)])
+    assert abs(S.intra(ov.apply_increment(x, topo, step)) - S.intra(x)) < 1e-10
+    step[6:] = rng.normal(size=topo.n_rot)
+    y = ov.apply_increment(x, topo, step)
+    lg = gold["G"]["ligand"]
+    for a, b in lg["bonds"]:
+        assert abs(np.linalg.norm(y[a] - y[b]) - np.linalg.norm(x[a] - x[b])) < 1e-9
+    for pc in set(topo.piece.tolist()):
+        m = np.where(topo.piece == pc)[0]
+        dx = np.linalg.norm(x[m][:, None] - x[m][None], axis=-1); dy = np.linalg.norm(y[m][:, None] - y[m][None], axis=-1)
+        assert np.abs(dx - dy).max() < 1e-9
+    # two torsions whose moving sets are disjoint commute
+    sets = [set(mv) for _, _, mv in topo.torsions]
+    i, j = next((i, j) for i in range(len(sets)) for j in range(i + 1, len(sets)) if not (sets[i] & sets[j]))
+    s1 = np.zeros(6 + topo.n_rot); s2 = np.zeros(6 + topo.n_rot); s1[6 + i] = 0.7; s2[6 + j] = -0.4
+    a = ov.apply_increment(ov.apply_increment(x, topo, s1), topo, s2); b = ov.apply_increment(ov.apply_increment(x, topo, s2), topo, s1)
+    assert np.abs(a - b).max() < 1e-9 and np.abs(a - ov.apply_increment(x, topo, s1 + s2)).max() < 1e-9
